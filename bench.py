@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Headline benchmark: GPT-2 small bf16 data-parallel training throughput (tokens/s) on N B200s.
+
+Contract (see task statement): ``python bench.py --gpus N --steps K --warmup W`` — for N > 1 it is
+launched under ``torch.distributed.run`` with one rank per GPU. Prints ONE JSON line on rank 0.
+
+* ``value``   device-timed (CUDA events, max over ranks) whole-job tokens/s of the full training step:
+              forward + backward + fused reduce-scatter/AdamW/all-gather, replayed as a CUDA graph.
+* ``e2e``     the same metric through the public API (``TrainStep.__call__``) including, every step, the
+              pinned-host -> device copy of that step's batch and a device -> host read of the loss.
+* ``--impl reference`` runs the unmodified reference from ``baseline/_ref`` if it can be imported
+              (it cannot in this image: it imports tensorflow/pyspark unconditionally) and otherwise
+              reports ``unavailable``.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch"])
+    ap.add_argument("--model", default="gpt2-small")
+    ap.add_argument("--batch", type=int, default=32, help="sequences per GPU per step")
+    ap.add_argument("--seq", type=int, default=1024)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-multicast", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def _pump():
+            for line in self.proc.stdout:
+                self.lines.append(line.strip())
+
+        self.thread = threading.Thread(target=_pump, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_arm(args):
+    """Run the UNMODIFIED reference through its own public API, or say why it cannot run."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    why = None
+    if not os.path.isdir(os.path.join(ref_dir, "maggy")):
+        why = "baseline/_ref/maggy not installed (pip --no-index install failed or was not run)"
+    else:
+        sys.path.insert(0, ref_dir)
+        try:
+            from maggy import experiment  # noqa: F401  (imports tensorflow + pyspark unconditionally)
+            from maggy.config import TorchDistributedConfig  # noqa: F401
+        except Exception as e:  # pragma: no cover - depends on the image
+            why = f"reference import fails: {type(e).__name__}: {str(e)[:160]}"
+    if why is None:
+        why = ("reference imports but its torch-distributed driver needs a Spark cluster "
+               "(pyspark) and is broken as written (_patching_fn arity, SURVEY.md 2.8)")
+    print(json.dumps({"impl": "reference", "unavailable": why}))
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    from maggy_b200.models.gpt2 import GPT2Config
+    from maggy_b200.ops import functional as F
+
+    cfg = GPT2Config.named(args.model)
+    B, T = args.batch, args.seq
+    K, W = args.steps, max(args.warmup, 3)
+
+    if args.impl == "ours":
+        from maggy_b200.parallel.trainer import build_gpt2_trainer
+
+        model, flat, opt, step = build_gpt2_trainer(
+            cfg, B, T, device, world_size=world, rank=rank, use_cuda_graph=not args.no_graph,
+            use_multicast=not args.no_multicast)
+        uses_mc = opt.uses_multicast
+    else:
+        step, uses_mc = build_torch_baseline(cfg, B, T, device, world, rank)
+
+    # a pool of pinned host batches (synthetic tokens): every step copies a different one
+    g = torch.Generator().manual_seed(1000 + rank)
+    pool = [(torch.randint(0, cfg.vocab_size, (B, T), generator=g).pin_memory(),
+             torch.randint(0, cfg.vocab_size, (B, T), generator=g).pin_memory()) for _ in range(4)]
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---------------- warm-up (includes CUDA-graph capture) ----------------
+    step.load_batch(*pool[0])
+    for i in range(W):
+        step()
+    sync_all()
+
+    # ---------------- device-timed region: exactly K steps -----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches_before = F.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for i in range(K):
+        step()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = float(step.loss.item())
+
+    # ---------------- end-to-end region through the public API -------------
+    h2d = sum(t.numel() * t.element_size() for t in pool[0])
+    d2h = 4
+    sync_all()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    f0.record()
+    host_losses = []
+    for i in range(K):
+        idx, tgt = pool[i % len(pool)]
+        loss = step(idx, tgt)          # pinned H2D copy + graph replay
+        host_losses.append(float(loss.item()))  # D2H read of the step's result
+    f1.record()
+    sync_all()
+    ms_e2e = f0.elapsed_time(f1)
+    wall_e2e_ms = (time.perf_counter() - t_wall0) * 1e3
+
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    tokens = B * T * world * K
+    value = tokens / (ms / 1e3)
+    e2e_value = tokens / (ms_e2e / 1e3)
+    if args.impl == "ours":
+        launches = step.kernels_per_step * K if not args.no_graph else F.launch_count() - launches_before
+    else:
+        launches = 0
+    out = {
+        "metric": "dist-train tokens/sec (GPT-2 small bf16 data-parallel, fused reduce-scatter+Adam)",
+        "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic random tokens, random-init weights",
+        "impl": args.impl,
+        "config": {"model": args.model, "params": sum(p.numel() for p in model.parameters()) if args.impl == "ours" else None,
+                   "global_batch": B * world, "seq_len": T, "per_gpu_batch": B,
+                   "parallelism": f"dp{world}" + ("+zero1-fused-rs-adam" if args.impl == "ours" else "+ddp+zero1"),
+                   "nvls_multicast": bool(uses_mc), "cuda_graph": not args.no_graph,
+                   "l2": "per-step working set (activations + logits, several GB) >> 126 MB L2; no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "tokens/s", "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "final_loss": final_loss,
+        "mfu_vs_measured_bf16_peak": None,
+    }
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        if args.impl == "ours":
+            fl = model.flops_per_token(T) * B * T / (ms / K / 1e3)  # per GPU
+            out["mfu_vs_measured_bf16_peak"] = fl / (peaks["bf16_tflops_sustained"] * 1e12)
+            out["model_tflops_per_gpu"] = fl / 1e12
+    except Exception:
+        pass
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def build_torch_baseline(cfg, B, T, device, world, rank):
+    """Stock-library arm (proxy of the reference's mechanisms): DDP + ZeroRedundancyOptimizer(AdamW)
+    over NCCL, cuBLAS/ATen kernels, bf16 autocast — what maggy's torch patching wires up
+    (maggy/core/patching/modules.py:44-63, optim.py:28-45)."""
+    import torch
+    import torch.distributed as dist
+
+    from maggy_b200.models.gpt2 import TorchGPT2
+
+    torch.manual_seed(1234)
+    model = TorchGPT2(cfg).to(device)
+    if world > 1:
+        from torch.distributed.optim import ZeroRedundancyOptimizer
+        from torch.nn.parallel import DistributedDataParallel as DDP
+
+        ddp = DDP(model, device_ids=[device.index])
+        opt = ZeroRedundancyOptimizer(ddp.parameters(), optimizer_class=torch.optim.AdamW, lr=3e-4,
+                                      betas=(0.9, 0.95), weight_decay=0.1, fused=True)
+    else:
+        ddp = model
+        opt = torch.optim.AdamW(model.parameters(), lr=3e-4, betas=(0.9, 0.95), weight_decay=0.1, fused=True)
+
+    class Step:
+        def __init__(self):
+            self.idx = torch.zeros((B, T), dtype=torch.long, device=device)
+            self.tgt = torch.zeros((B, T), dtype=torch.long, device=device)
+            self.loss = torch.zeros((), device=device)
+            self.kernels_per_step = 0
+
+        def load_batch(self, idx, tgt):
+            self.idx.copy_(idx, non_blocking=True)
+            self.tgt.copy_(tgt, non_blocking=True)
+
+        def __call__(self, idx=None, tgt=None):
+            if idx is not None:
+                self.load_batch(idx, tgt)
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = ddp(self.idx, self.tgt)
+            loss.backward()
+            opt.step()
+            self.loss.copy_(loss.detach())
+            return self.loss
+
+    return Step(), False
+
+
+if __name__ == "__main__":
+    sys.exit(main())

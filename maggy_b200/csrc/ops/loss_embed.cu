@@ -1,0 +1,325 @@
+// Fused softmax-cross-entropy (forward + backward in one pass over a shared-memory resident row),
+// column-sum (bias gradients), GELU, and token/position embedding kernels for sm_100a.
+// All are HBM-bound: 16-byte vector accesses, one read + one write of the big operand.
+#include "../include/mg_ptx.cuh"
+
+namespace {
+using namespace mg;
+
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* scratch) {
+  v = is_max ? warp_max(v) : warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float r = (lane < nwarps) ? scratch[lane] : (is_max ? -INFINITY : 0.f);
+  r = is_max ? warp_max(r) : warp_sum(r);
+  return r;
+}
+
+// logits [rows, ld] bf16 are overwritten with d(mean loss)/d(logits) * grad_scale.
+// losses[row] = per-row NLL (0 for ignored rows). Columns >= v_real are padding.
+__global__ void __launch_bounds__(256)
+ce_fwd_bwd_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restrict__ targets,
+                  float* __restrict__ losses, int v_real, int v_pad, long long ld,
+                  float grad_scale, int ignore_index) {
+  extern __shared__ __align__(16) uint8_t smem_row[];
+  __shared__ float scratch[32];
+  uint4* srow = reinterpret_cast<uint4*>(smem_row);
+  const int row = blockIdx.x;
+  uint4* grow = reinterpret_cast<uint4*>(logits + static_cast<size_t>(row) * ld);
+  const int nvec = v_pad >> 3;
+  const long long tgt = targets[row];
+  const bool ignored = (tgt == ignore_index) || tgt < 0 || tgt >= v_real;
+
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    uint4 u = ld_nc_v4(grow + i);
+    srow[i] = u;
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 f = unpack_bf16x2(w[t]);
+      int c = i * 8 + 2 * t;
+      if (c < v_real) mx = fmaxf(mx, f.x);
+      if (c + 1 < v_real) mx = fmaxf(mx, f.y);
+    }
+  }
+  mx = block_reduce(mx, true, scratch);
+  const float kLog2e = 1.4426950408889634f;
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    uint4 u = srow[i];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 f = unpack_bf16x2(w[t]);
+      int c = i * 8 + 2 * t;
+      if (c < v_real) sum += exp2f((f.x - mx) * kLog2e);
+      if (c + 1 < v_real) sum += exp2f((f.y - mx) * kLog2e);
+    }
+  }
+  sum = block_reduce(sum, false, scratch);
+  const float inv_sum = 1.0f / sum;
+  if (threadIdx.x == 0) {
+    float loss = 0.f;
+    if (!ignored) {
+      float xt = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(smem_row)[tgt]);
+      loss = logf(sum) + mx - xt;
+    }
+    losses[row] = loss;
+  }
+  const float gs = ignored ? 0.f : grad_scale;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    uint4 u = srow[i];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 f = unpack_bf16x2(w[t]);
+      int c = i * 8 + 2 * t;
+      float p0 = (c < v_real) ? exp2f((f.x - mx) * kLog2e) * inv_sum : 0.f;
+      float p1 = (c + 1 < v_real) ? exp2f((f.y - mx) * kLog2e) * inv_sum : 0.f;
+      if (c == tgt) p0 -= 1.0f;
+      if (c + 1 == tgt) p1 -= 1.0f;
+      o[t] = pack_bf16x2(p0 * gs, p1 * gs);
+    }
+    st_na_v4(grow + i, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// partial[blockIdx.y][n] = sum over this slab's rows of x[row][n]
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, long long ld,
+                      float* __restrict__ partial) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vcol = blockIdx.x * 32 + lane;  // vector column (8 elements)
+  const bool ok = vcol * 8 < N;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int rows_per_slab = (M + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per_slab;
+  const int r1 = min(M, r0 + rows_per_slab);
+  if (ok) {
+    for (int r = r0 + warp; r < r1; r += 8) {
+      uint4 u = ld_nc_v4(reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * ld) + vcol);
+      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
+             d = unpack_bf16x2(u.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+      acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
+  }
+  __shared__ float red[8][32][9];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) red[warp][lane][t] = acc[t];
+  __syncthreads();
+  // thread (warp w, lane l) finalises element t = w of vector column l
+  if (ok) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][lane][warp];
+    partial[static_cast<size_t>(blockIdx.y) * N + vcol * 8 + warp] = s;
+  }
+}
+
+__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nslabs, int N,
+                                       __nv_bfloat16* __restrict__ out, int accumulate) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int i = 0; i < nslabs; ++i) s += partial[static_cast<size_t>(i) * N + n];
+  if (accumulate) s += __bfloat162float(out[n]);
+  out[n] = __float2bfloat16(s);
+}
+
+__global__ void __launch_bounds__(256)
+gelu_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  const long long nvec = n >> 3;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint4 u = ld_nc_v4(reinterpret_cast<const uint4*>(x) + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 f = unpack_bf16x2(w[t]);
+      o[t] = pack_bf16x2(gelu_tanh(f.x), gelu_tanh(f.y));
+    }
+    st_na_v4(reinterpret_cast<uint4*>(y) + i, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                __nv_bfloat16* __restrict__ dx, long long n) {
+  const long long nvec = n >> 3;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint4 u = ld_nc_v4(reinterpret_cast<const uint4*>(x) + i);
+    uint4 g = ld_nc_v4(reinterpret_cast<const uint4*>(dy) + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w}, gw[4] = {g.x, g.y, g.z, g.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 f = unpack_bf16x2(w[t]), d = unpack_bf16x2(gw[t]);
+      o[t] = pack_bf16x2(d.x * dgelu_tanh(f.x), d.y * dgelu_tanh(f.y));
+    }
+    st_na_v4(reinterpret_cast<uint4*>(dx) + i, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// out[t, :] = wte[idx[t], :] + wpe[t % T, :]
+__global__ void __launch_bounds__(128)
+embed_fwd_kernel(const long long* __restrict__ idx, const __nv_bfloat16* __restrict__ wte,
+                 const __nv_bfloat16* __restrict__ wpe, __nv_bfloat16* __restrict__ out, int ntok,
+                 int T, int C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tok = blockIdx.x * 4 + warp;
+  if (tok >= ntok) return;
+  const long long id = idx[tok];
+  const uint4* te = reinterpret_cast<const uint4*>(wte + static_cast<size_t>(id) * C);
+  const uint4* pe = reinterpret_cast<const uint4*>(wpe + static_cast<size_t>(tok % T) * C);
+  uint4* o = reinterpret_cast<uint4*>(out + static_cast<size_t>(tok) * C);
+  for (int v = lane; v < (C >> 3); v += 32) {
+    uint4 a = __ldg(te + v), b = __ldg(pe + v);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 fa = unpack_bf16x2(aw[t]), fb = unpack_bf16x2(bw[t]);
+      r[t] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+    }
+    o[v] = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// dwte[idx[t], :] += dout[t, :]   (bf16x2 reductions; dwte already holds the tied LM-head wgrad)
+// dwpe[p, :]      = sum_b dout[b*T + p, :]   (one warp per position, deterministic)
+__global__ void __launch_bounds__(128)
+embed_bwd_wte_kernel(const long long* __restrict__ idx, const __nv_bfloat16* __restrict__ dout,
+                     __nv_bfloat16* __restrict__ dwte, int ntok, int C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tok = blockIdx.x * 4 + warp;
+  if (tok >= ntok) return;
+  const long long id = idx[tok];
+  const __nv_bfloat162* src = reinterpret_cast<const __nv_bfloat162*>(dout + static_cast<size_t>(tok) * C);
+  __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(dwte + static_cast<size_t>(id) * C);
+  for (int v = lane; v < (C >> 1); v += 32) atomicAdd(dst + v, src[v]);
+}
+
+__global__ void __launch_bounds__(128)
+embed_bwd_wpe_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dwpe, int B,
+                     int T, int C, int accumulate) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pos = blockIdx.x * 4 + warp;
+  if (pos >= T) return;
+  for (int v = lane; v < (C >> 3); v += 32) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < B; ++b) {
+      uint4 u = ld_nc_v4(reinterpret_cast<const uint4*>(dout + (static_cast<size_t>(b) * T + pos) * C) + v);
+      float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
+             d = unpack_bf16x2(u.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += bb.x; acc[3] += bb.y;
+      acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(dwpe + static_cast<size_t>(pos) * C) + v;
+    if (accumulate) {
+      uint4 u = *dst;
+      float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
+             d = unpack_bf16x2(u.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += bb.x; acc[3] += bb.y;
+      acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
+    *dst = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                      pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+inline int grid_for(long long nvec) {
+  long long g = (nvec + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+inline int check() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
+}
+
+}  // namespace
+
+extern "C" int mg_ce_fwd_bwd(void* logits, const long long* targets, float* losses, int rows,
+                             int v_real, int v_pad, long long ld, float grad_scale,
+                             int ignore_index, void* stream) {
+  if (v_pad % 8 != 0 || ld % 8 != 0) return -1;
+  size_t smem = static_cast<size_t>(v_pad) * 2;
+  if (smem > 200 * 1024) return -2;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(ce_fwd_bwd_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return -300 - static_cast<int>(e);
+    configured = smem;
+  }
+  ce_fwd_bwd_kernel<<<rows, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(logits), targets, losses, v_real, v_pad, ld, grad_scale,
+      ignore_index);
+  return check();
+}
+
+extern "C" int mg_colsum_slabs(int M) {
+  int s = (M + 255) / 256;
+  return s < 1 ? 1 : (s > 64 ? 64 : s);
+}
+
+// partial: fp32 scratch of mg_colsum_slabs(M) * N floats
+extern "C" int mg_colsum_bf16(const void* x, int M, int N, long long ld, void* out, float* partial,
+                              int accumulate, void* stream) {
+  if (N % 8 != 0 || ld % 8 != 0) return -1;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int slabs = mg_colsum_slabs(M);
+  dim3 grid((N / 8 + 31) / 32, slabs);
+  colsum_partial_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, N, ld,
+                                             partial);
+  colsum_finalize_kernel<<<(N + 255) / 256, 256, 0, s>>>(partial, slabs, N,
+                                                         reinterpret_cast<__nv_bfloat16*>(out),
+                                                         accumulate);
+  return check();
+}
+
+extern "C" int mg_gelu_fwd(const void* x, void* y, long long n, void* stream) {
+  if (n % 8 != 0) return -1;
+  gelu_fwd_kernel<<<grid_for(n >> 3), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), n);
+  return check();
+}
+
+extern "C" int mg_gelu_bwd(const void* x, const void* dy, void* dx, long long n, void* stream) {
+  if (n % 8 != 0) return -1;
+  gelu_bwd_kernel<<<grid_for(n >> 3), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy),
+      reinterpret_cast<__nv_bfloat16*>(dx), n);
+  return check();
+}
+
+extern "C" int mg_embed_fwd(const long long* idx, const void* wte, const void* wpe, void* out,
+                            int ntok, int T, int C, void* stream) {
+  if (C % 8 != 0) return -1;
+  embed_fwd_kernel<<<(ntok + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      idx, reinterpret_cast<const __nv_bfloat16*>(wte), reinterpret_cast<const __nv_bfloat16*>(wpe),
+      reinterpret_cast<__nv_bfloat16*>(out), ntok, T, C);
+  return check();
+}
+
+extern "C" int mg_embed_bwd(const long long* idx, const void* dout, void* dwte, void* dwpe, int B,
+                            int T, int C, int accumulate_wpe, void* stream) {
+  if (C % 8 != 0) return -1;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  embed_bwd_wte_kernel<<<(B * T + 3) / 4, 128, 0, s>>>(
+      idx, reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<__nv_bfloat16*>(dwte),
+      B * T, C);
+  embed_bwd_wpe_kernel<<<(T + 3) / 4, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dout),
+                                                   reinterpret_cast<__nv_bfloat16*>(dwpe), B, T, C,
+                                                   accumulate_wpe);
+  return check();
+}

@@ -1,0 +1,244 @@
+// K6 — fused LayerNorm / RMSNorm forward + backward for sm_100a (bf16 I/O, fp32 math).
+//
+// Bandwidth-bound: one warp owns one row, the row stays in registers between the statistics pass
+// and the normalise pass (one HBM read, one HBM write), 16-byte vector accesses, no shared memory in
+// forward. Backward keeps per-lane dgamma/dbeta partials in registers across a persistent loop over
+// rows and writes one partial row per CTA; a second tiny kernel folds the partials.
+// Stands in for the cuDNN/ATen norm kernels the reference reaches through train_fn.
+#include "../include/mg_ptx.cuh"
+
+namespace {
+using namespace mg;
+
+constexpr int kMaxVec = 16;  // up to 16 * 32 lanes * 8 = 4096 columns held in registers
+
+template <bool RMS>
+__global__ void __launch_bounds__(128)
+norm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int C,
+                float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= rows) return;
+  const int nvec = C >> 3;  // uint4 vectors per row
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * C);
+  uint4 buf[kMaxVec];
+  float s = 0.f, ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    int v = lane + i * 32;
+    if (v < nvec) {
+      buf[i] = ld_nc_v4(xr + v);
+      float2 a = unpack_bf16x2(buf[i].x), b = unpack_bf16x2(buf[i].y), c = unpack_bf16x2(buf[i].z),
+             d = unpack_bf16x2(buf[i].w);
+      s += a.x + a.y + b.x + b.y + c.x + c.y + d.x + d.y;
+      ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x +
+            d.y * d.y;
+    }
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  const float inv_c = 1.0f / static_cast<float>(C);
+  float mean = RMS ? 0.f : s * inv_c;
+  float var = RMS ? ss * inv_c : fmaxf(ss * inv_c - mean * mean, 0.f);
+  float rstd = rsqrtf(var + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+  uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * C);
+  const uint4* g4 = reinterpret_cast<const uint4*>(gamma);
+  const uint4* b4 = reinterpret_cast<const uint4*>(beta);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    int v = lane + i * 32;
+    if (v < nvec) {
+      uint4 g = __ldg(g4 + v);
+      uint4 b = (RMS || beta == nullptr) ? make_uint4(0, 0, 0, 0) : __ldg(b4 + v);
+      const uint32_t xi[4] = {buf[i].x, buf[i].y, buf[i].z, buf[i].w};
+      const uint32_t gi[4] = {g.x, g.y, g.z, g.w};
+      const uint32_t bi[4] = {b.x, b.y, b.z, b.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 xv = unpack_bf16x2(xi[t]), gv = unpack_bf16x2(gi[t]), bv = unpack_bf16x2(bi[t]);
+        o[t] = pack_bf16x2((xv.x - mean) * rstd * gv.x + bv.x, (xv.y - mean) * rstd * gv.y + bv.y);
+      }
+      st_na_v4(yr + v, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+  }
+}
+
+// dx = rstd * (g*dy - mean_c(g*dy) - xhat * mean_c(g*dy*xhat))      (LayerNorm)
+// dx = rstd * (g*dy - xhat * mean_c(g*dy*xhat))                     (RMSNorm)
+// partial[blockIdx.x][0][c] = sum_rows dy*xhat ; partial[blockIdx.x][1][c] = sum_rows dy
+template <bool RMS, int NVEC>
+__global__ void __launch_bounds__(128)
+norm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean_in,
+                const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dx,
+                float* __restrict__ partial, int rows, int C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  float dg[NVEC][8], db[NVEC][8];
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) dg[i][t] = db[i][t] = 0.f;
+  const uint4* g4 = reinterpret_cast<const uint4*>(gamma);
+  const float inv_c = 1.0f / static_cast<float>(C);
+
+  for (int row = blockIdx.x * 4 + warp; row < rows; row += gridDim.x * 4) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * C);
+    const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * C);
+    uint4* dxr = reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * C);
+    const float mean = RMS ? 0.f : mean_in[row];
+    const float rstd = rstd_in[row];
+    float xh[NVEC][8], gy[NVEC][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      int v = lane + i * 32;
+      if (v < nvec) {
+        uint4 xv = ld_nc_v4(xr + v), dv = ld_nc_v4(dyr + v), gv = __ldg(g4 + v);
+        const uint32_t xi[4] = {xv.x, xv.y, xv.z, xv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w},
+                       gi[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float2 xf = unpack_bf16x2(xi[t]), df = unpack_bf16x2(di[t]), gf = unpack_bf16x2(gi[t]);
+          float h0 = (xf.x - mean) * rstd, h1 = (xf.y - mean) * rstd;
+          xh[i][2 * t] = h0; xh[i][2 * t + 1] = h1;
+          gy[i][2 * t] = gf.x * df.x; gy[i][2 * t + 1] = gf.y * df.y;
+          dg[i][2 * t] += df.x * h0; dg[i][2 * t + 1] += df.y * h1;
+          db[i][2 * t] += df.x; db[i][2 * t + 1] += df.y;
+          s1 += gy[i][2 * t] + gy[i][2 * t + 1];
+          s2 += gy[i][2 * t] * h0 + gy[i][2 * t + 1] * h1;
+        }
+      }
+    }
+    s1 = RMS ? 0.f : warp_sum(s1) * inv_c;
+    s2 = warp_sum(s2) * inv_c;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      int v = lane + i * 32;
+      if (v < nvec) {
+        uint32_t o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float a = rstd * (gy[i][2 * t] - s1 - xh[i][2 * t] * s2);
+          float b = rstd * (gy[i][2 * t + 1] - s1 - xh[i][2 * t + 1] * s2);
+          o[t] = pack_bf16x2(a, b);
+        }
+        st_na_v4(dxr + v, make_uint4(o[0], o[1], o[2], o[3]));
+      }
+    }
+  }
+
+  // fold the 4 warps of this CTA through shared memory, then one partial row per CTA
+  extern __shared__ float red[];  // [4][2][C]
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    int v = lane + i * 32;
+    if (v < nvec) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        red[(warp * 2 + 0) * C + v * 8 + t] = dg[i][t];
+        red[(warp * 2 + 1) * C + v * 8 + t] = db[i][t];
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    int which = c / C, col = c - which * C;
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) acc += red[(w * 2 + which) * C + col];
+    partial[(static_cast<size_t>(blockIdx.x) * 2 + which) * C + col] = acc;
+  }
+}
+
+__global__ void norm_bwd_finalize_kernel(const float* __restrict__ partial, int nparts, int C,
+                                         __nv_bfloat16* __restrict__ dgamma,
+                                         __nv_bfloat16* __restrict__ dbeta, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 2 * C) return;
+  int which = c / C, col = c - which * C;
+  float acc = 0.f;
+  for (int pidx = 0; pidx < nparts; ++pidx)
+    acc += partial[(static_cast<size_t>(pidx) * 2 + which) * C + col];
+  __nv_bfloat16* dst = which == 0 ? dgamma : dbeta;
+  if (dst == nullptr) return;
+  if (accumulate) acc += __bfloat162float(dst[col]);
+  dst[col] = __float2bfloat16(acc);
+}
+
+template <bool RMS>
+int launch_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
+               const float* rstd, void* dx, float* partial, int rows, int C, int grid,
+               cudaStream_t s) {
+  const int nvec_lane = ((C >> 3) + 31) / 32;
+  size_t smem = static_cast<size_t>(8) * C * sizeof(float);
+#define MG_BWD_CASE(NV)                                                                            \
+  {                                                                                                \
+    auto k = norm_bwd_kernel<RMS, NV>;                                                             \
+    if (smem > 48 * 1024)                                                                          \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+    k<<<grid, 128, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy),                           \
+                              reinterpret_cast<const __nv_bfloat16*>(x),                            \
+                              reinterpret_cast<const __nv_bfloat16*>(gamma), mean, rstd,            \
+                              reinterpret_cast<__nv_bfloat16*>(dx), partial, rows, C);              \
+  }
+  if (nvec_lane <= 1) MG_BWD_CASE(1)
+  else if (nvec_lane <= 2) MG_BWD_CASE(2)
+  else if (nvec_lane <= 3) MG_BWD_CASE(3)
+  else if (nvec_lane <= 4) MG_BWD_CASE(4)
+  else if (nvec_lane <= 8) MG_BWD_CASE(8)
+  else return -1;
+#undef MG_BWD_CASE
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
+}
+
+}  // namespace
+
+// rms: 0 = LayerNorm (mean/rstd saved), 1 = RMSNorm (rstd saved, beta ignored). C % 8 == 0, C <= 4096.
+extern "C" int mg_norm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean,
+                           float* rstd, int rows, int C, float eps, int rms, void* stream) {
+  if (C % 8 != 0 || C > kMaxVec * 256) return -1;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int grid = (rows + 3) / 4;
+  if (rms)
+    norm_fwd_kernel<true><<<grid, 128, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(gamma),
+        nullptr, reinterpret_cast<__nv_bfloat16*>(y), nullptr, rstd, rows, C, eps);
+  else
+    norm_fwd_kernel<false><<<grid, 128, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(gamma),
+        reinterpret_cast<const __nv_bfloat16*>(beta), reinterpret_cast<__nv_bfloat16*>(y), mean,
+        rstd, rows, C, eps);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
+}
+
+// partial: fp32 scratch of at least mg_norm_bwd_grid(rows) * 2 * C floats. C % 8 == 0, C <= 2048.
+extern "C" int mg_norm_bwd_grid(int rows) {
+  int g = (rows + 3) / 4;
+  return g < 592 ? g : 592;  // 148 SMs x 4 resident CTAs
+}
+
+extern "C" int mg_norm_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
+                           const float* rstd, void* dx, void* dgamma, void* dbeta, float* partial,
+                           int rows, int C, int rms, int accumulate, void* stream) {
+  if (C % 8 != 0 || C > 2048) return -1;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int grid = mg_norm_bwd_grid(rows);
+  int rc = rms ? launch_bwd<true>(dy, x, gamma, mean, rstd, dx, partial, rows, C, grid, s)
+               : launch_bwd<false>(dy, x, gamma, mean, rstd, dx, partial, rows, C, grid, s);
+  if (rc) return rc;
+  norm_bwd_finalize_kernel<<<(2 * C + 255) / 256, 256, 0, s>>>(
+      partial, grid, C, reinterpret_cast<__nv_bfloat16*>(dgamma),
+      rms ? nullptr : reinterpret_cast<__nv_bfloat16*>(dbeta), accumulate);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
+}

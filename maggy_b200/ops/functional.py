@@ -1,0 +1,410 @@
+"""Python front-end of the hand-written sm_100a kernels (``csrc/ops``).
+
+Two layers:
+
+* thin launchers (``gemm``, ``layer_norm_fwd`` ...) that validate shapes/strides and call the C ABI of
+  ``libmaggy_b200_cuda.so`` on the current torch CUDA stream (so they are CUDA-graph capturable);
+* ``torch.autograd.Function`` wrappers (``linear``, ``layer_norm``, ``mlp``, ``cross_entropy``,
+  ``embedding``) whose backward also runs on the hand-written kernels.
+
+Weight gradients follow the *main_grad* convention: if a parameter has a ``main_grad`` attribute (a
+view into the flat gradient arena owned by ``maggy_b200.parallel``), wgrad kernels write straight
+into it and autograd sees ``None`` — no per-parameter ``.grad`` tensors, no accumulate kernels, and
+the arena is exactly the buffer the fused reduce-scatter+Adam kernel consumes.
+
+These ops require CUDA: calling them on CPU tensors raises (tests use plain PyTorch as the fp32
+reference, never as a fallback).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_BIAS_RESIDUAL = 0, 1, 2, 3, 4
+K_MAJOR, MN_MAJOR = 0, 1
+
+_scratch: dict = {}
+_launches = 0  # hand-written kernels launched through this module (bench.py reports it)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _count(n: int = 1):
+    global _launches
+    _launches += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("maggy_b200 ops run on CUDA tensors only (sm_100a kernels); got a CPU tensor")
+
+
+def _scratch_f32(key: str, numel: int, device) -> torch.Tensor:
+    """Reusable fp32 workspace (stable address => CUDA-graph safe as long as sizes are stable)."""
+    k = (key, device)
+    buf = _scratch.get(k)
+    if buf is None or buf.numel() < numel:
+        buf = torch.empty(max(numel, 1), dtype=torch.float32, device=device)
+        _scratch[k] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------
+# thin launchers
+# ------------------------------------------------------------------------------------------------
+def gemm(a, b, *, a_major=K_MAJOR, b_major=K_MAJOR, bias=None, aux=None, epi=EPI_NONE, out=None,
+         out_dtype=torch.bfloat16, accumulate=False, block_n=0, sm_limit=0):
+    """``C[M,N] = epi(sum_k A(m,k) B(n,k))`` on the tcgen05 kernel.
+
+    ``a`` is ``[M,K]`` (``a_major=K_MAJOR``) or ``[K,M]`` (``MN_MAJOR``); ``b`` is ``[N,K]`` or ``[K,N]``.
+    Rows may be strided (``stride(0)`` multiple of 8 elements), the inner dimension must be contiguous.
+    """
+    _need_cuda(a, b, bias, aux, out)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16, "bf16 operands"
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = (a.shape[0], a.shape[1]) if a_major == K_MAJOR else (a.shape[1], a.shape[0])
+    N, Kb = (b.shape[0], b.shape[1]) if b_major == K_MAJOR else (b.shape[1], b.shape[0])
+    assert K == Kb, f"reduction mismatch {K} vs {Kb}"
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    assert out.dtype in (torch.bfloat16, torch.float32)
+    ld_aux = 0
+    if epi in (EPI_BIAS_GELU, EPI_DGELU, EPI_BIAS_RESIDUAL):
+        assert aux is not None and aux.shape == (M, N) and aux.stride(1) == 1 and aux.dtype == torch.bfloat16
+        ld_aux = aux.stride(0)
+    if bias is not None:
+        assert bias.dtype == torch.bfloat16 and bias.numel() == N and bias.is_contiguous()
+    rc = _lib.cuda().mg_gemm_bf16(
+        a.data_ptr(), b.data_ptr(), out.data_ptr(), _ptr(bias), _ptr(aux), M, N, K,
+        a.stride(0), b.stride(0), out.stride(0), ld_aux, a_major, b_major, epi,
+        1 if out.dtype == torch.float32 else 0, 1 if accumulate else 0, block_n, sm_limit, _stream())
+    _lib.check(rc, f"mg_gemm_bf16(M={M},N={N},K={K})")
+    _count(1)
+    return out
+
+
+def layer_norm_fwd(x2d, weight, bias, eps=1e-5, rms=False):
+    _need_cuda(x2d, weight, bias)
+    rows, C = x2d.shape
+    assert x2d.is_contiguous() and x2d.dtype == torch.bfloat16
+    y = torch.empty_like(x2d)
+    mean = None if rms else torch.empty(rows, dtype=torch.float32, device=x2d.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x2d.device)
+    rc = _lib.cuda().mg_norm_fwd(x2d.data_ptr(), weight.data_ptr(), _ptr(bias), y.data_ptr(),
+                                 _ptr(mean), rstd.data_ptr(), rows, C, eps, 1 if rms else 0, _stream())
+    _lib.check(rc, "mg_norm_fwd")
+    _count(1)
+    return y, mean, rstd
+
+
+def layer_norm_bwd(dy2d, x2d, weight, mean, rstd, dgamma, dbeta, rms=False, accumulate=False):
+    _need_cuda(dy2d, x2d)
+    rows, C = x2d.shape
+    dy2d = dy2d.contiguous()
+    dx = torch.empty_like(x2d)
+    lib = _lib.cuda()
+    grid = lib.mg_norm_bwd_grid(rows)
+    partial = _scratch_f32("norm_bwd", grid * 2 * C, x2d.device)
+    rc = lib.mg_norm_bwd(dy2d.data_ptr(), x2d.data_ptr(), weight.data_ptr(), _ptr(mean),
+                         rstd.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), _ptr(dbeta),
+                         partial.data_ptr(), rows, C, 1 if rms else 0, 1 if accumulate else 0, _stream())
+    _lib.check(rc, "mg_norm_bwd")
+    _count(2)
+    return dx
+
+
+def colsum(x2d, out, accumulate=False):
+    """out[n] (+)= sum_m x2d[m, n] — bias gradients."""
+    _need_cuda(x2d, out)
+    M, N = x2d.shape
+    assert x2d.stride(1) == 1 and out.numel() == N
+    lib = _lib.cuda()
+    partial = _scratch_f32("colsum", lib.mg_colsum_slabs(M) * N, x2d.device)
+    rc = lib.mg_colsum_bf16(x2d.data_ptr(), M, N, x2d.stride(0), out.data_ptr(), partial.data_ptr(),
+                            1 if accumulate else 0, _stream())
+    _lib.check(rc, "mg_colsum_bf16")
+    _count(2)
+    return out
+
+
+def gelu_fwd(x):
+    _need_cuda(x)
+    y = torch.empty_like(x)
+    _lib.check(_lib.cuda().mg_gelu_fwd(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "mg_gelu_fwd")
+    _count(1)
+    return y
+
+
+def gelu_bwd(x, dy):
+    _need_cuda(x, dy)
+    dx = torch.empty_like(x)
+    _lib.check(_lib.cuda().mg_gelu_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), _stream()),
+               "mg_gelu_bwd")
+    _count(1)
+    return dx
+
+
+def adam_flat_step(master, m, v, grad_bf16, param_bf16, *, decay_boundary, lr, beta1, beta2, eps,
+                   weight_decay, step, grad_scale=1.0, gnorm_sq=None, max_norm=0.0, step_tensor=None,
+                   lr_tensor=None):
+    _need_cuda(master, m, v, grad_bf16, param_bf16)
+    n = master.numel()
+    rc = _lib.cuda().mg_adam_flat(master.data_ptr(), m.data_ptr(), v.data_ptr(), grad_bf16.data_ptr(),
+                                  param_bf16.data_ptr(), n, decay_boundary, lr, beta1, beta2, eps,
+                                  weight_decay, step, grad_scale, _ptr(gnorm_sq), max_norm,
+                                  _ptr(step_tensor), _ptr(lr_tensor), _stream())
+    _lib.check(rc, "mg_adam_flat")
+    _count(1)
+
+
+def sumsq(x_bf16, out_f32):
+    _need_cuda(x_bf16, out_f32)
+    out_f32.zero_()
+    _lib.check(_lib.cuda().mg_sumsq_bf16(x_bf16.data_ptr(), x_bf16.numel(), out_f32.data_ptr(), _stream()),
+               "mg_sumsq_bf16")
+    _count(1)
+    return out_f32
+
+
+def _write_or_return_grad(param, compute_into):
+    """main_grad convention. ``compute_into(dst, accumulate)`` must fill ``dst``."""
+    mg = getattr(param, "main_grad", None)
+    if mg is not None:
+        acc = bool(getattr(param, "_mg_written", False))
+        compute_into(mg, acc)
+        param._mg_written = True
+        return None
+    dst = torch.empty_like(param)
+    compute_into(dst, False)
+    return dst
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd functions
+# ------------------------------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b with tcgen05 fprop / dgrad / wgrad. Optional fused residual add."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual):
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        if residual is not None:
+            r2 = residual.reshape(-1, weight.shape[0])
+            y = gemm(x2, weight, bias=bias, aux=r2, epi=EPI_BIAS_RESIDUAL)
+        else:
+            y = gemm(x2, weight, bias=bias, epi=EPI_BIAS if bias is not None else EPI_NONE)
+        ctx.save_for_backward(x2, weight)
+        ctx.bias = bias
+        ctx.weight_ref = weight
+        ctx.has_res = residual is not None
+        ctx.xshape = x.shape
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dy2, weight, b_major=MN_MAJOR).view(ctx.xshape)
+        dw = _write_or_return_grad(
+            ctx.weight_ref,
+            lambda dst, acc: gemm(dy2, x2, a_major=MN_MAJOR, b_major=MN_MAJOR, out=dst, accumulate=acc))
+        db = None
+        if ctx.bias is not None:
+            db = _write_or_return_grad(ctx.bias, lambda dst, acc: colsum(dy2, dst, accumulate=acc))
+        dres = dy if ctx.has_res else None
+        return dx, dw, db, dres
+
+
+def linear(x, weight, bias=None, residual=None):
+    return _Linear.apply(x, weight, bias, residual)
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, rms):
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        y, mean, rstd = layer_norm_fwd(x2, weight, bias, eps, rms)
+        ctx.save_for_backward(x2, weight, mean if mean is not None else rstd, rstd)
+        ctx.w_ref, ctx.b_ref, ctx.rms = weight, bias, rms
+        ctx.xshape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, mean, rstd = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        w, b = ctx.w_ref, ctx.b_ref
+        use_main = getattr(w, "main_grad", None) is not None
+        if use_main:
+            acc = bool(getattr(w, "_mg_written", False))
+            dgamma = w.main_grad
+            dbeta = b.main_grad if b is not None else None
+            w._mg_written = True
+            if b is not None:
+                b._mg_written = True
+        else:
+            acc = False
+            dgamma = torch.empty_like(w)
+            dbeta = torch.empty_like(b) if b is not None else None
+        dx = layer_norm_bwd(dy2, x2, weight, None if ctx.rms else mean, rstd, dgamma, dbeta,
+                            rms=ctx.rms, accumulate=acc)
+        if use_main:
+            return dx.view(ctx.xshape), None, None, None, None
+        return dx.view(ctx.xshape), dgamma, dbeta, None, None
+
+
+def layer_norm(x, weight, bias, eps=1e-5):
+    return _LayerNorm.apply(x, weight, bias, eps, False)
+
+
+def rms_norm(x, weight, eps=1e-6):
+    return _LayerNorm.apply(x, weight, None, eps, True)
+
+
+class _MLP(torch.autograd.Function):
+    """out = residual + W2 gelu(W1 x + b1) + b2, GELU/dGELU/residual fused into GEMM epilogues."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual):
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        pre = torch.empty((M, w1.shape[0]), dtype=torch.bfloat16, device=x.device)
+        act = gemm(x2, w1, bias=b1, aux=pre, epi=EPI_BIAS_GELU)
+        if residual is not None:
+            r2 = residual.reshape(-1, w2.shape[0])
+            out = gemm(act, w2, bias=b2, aux=r2, epi=EPI_BIAS_RESIDUAL)
+        else:
+            out = gemm(act, w2, bias=b2, epi=EPI_BIAS)
+        ctx.save_for_backward(x2, pre, act)
+        ctx.refs = (w1, b1, w2, b2)
+        ctx.has_res = residual is not None
+        ctx.xshape = x.shape
+        return out.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, pre, act = ctx.saved_tensors
+        w1, b1, w2, b2 = ctx.refs
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        # d_pre = (dy W2) * gelu'(pre): dGELU fused into the dgrad epilogue
+        dpre = gemm(dy2, w2, b_major=MN_MAJOR, aux=pre, epi=EPI_DGELU)
+        dw2 = _write_or_return_grad(
+            w2, lambda dst, acc: gemm(dy2, act, a_major=MN_MAJOR, b_major=MN_MAJOR, out=dst, accumulate=acc))
+        db2 = _write_or_return_grad(b2, lambda dst, acc: colsum(dy2, dst, accumulate=acc))
+        dx = gemm(dpre, w1, b_major=MN_MAJOR).view(ctx.xshape)
+        dw1 = _write_or_return_grad(
+            w1, lambda dst, acc: gemm(dpre, x2, a_major=MN_MAJOR, b_major=MN_MAJOR, out=dst, accumulate=acc))
+        db1 = _write_or_return_grad(b1, lambda dst, acc: colsum(dpre, dst, accumulate=acc))
+        return dx, dw1, db1, dw2, db2, (dy if ctx.has_res else None)
+
+
+def mlp(x, w1, b1, w2, b2, residual=None):
+    return _MLP.apply(x, w1, b1, w2, b2, residual)
+
+
+class _CrossEntropy(torch.autograd.Function):
+    """mean NLL over non-ignored rows; the logits buffer is overwritten with its own gradient."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, v_real, ignore_index, unit_grad):
+        l2 = logits.reshape(-1, logits.shape[-1])
+        assert l2.stride(1) == 1
+        t = targets.reshape(-1)
+        rows, v_pad = l2.shape
+        losses = torch.empty(rows, dtype=torch.float32, device=logits.device)
+        rc = _lib.cuda().mg_ce_fwd_bwd(l2.data_ptr(), t.data_ptr(), losses.data_ptr(), rows, v_real,
+                                       v_pad, l2.stride(0), 1.0 / rows, ignore_index, _stream())
+        _lib.check(rc, "mg_ce_fwd_bwd")
+        _count(1)
+        ctx.save_for_backward(l2)
+        ctx.lshape = logits.shape
+        ctx.unit = unit_grad
+        return losses.sum() / rows
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dlogits,) = ctx.saved_tensors
+        # unit_grad=True (the training-step case: loss.backward()) skips a 2x|logits| scaling pass
+        g = dlogits.view(ctx.lshape)
+        if not ctx.unit:
+            g = g * dloss.to(g.dtype)
+        return g, None, None, None, None
+
+
+def cross_entropy(logits, targets, v_real=None, ignore_index=-100, unit_grad=True):
+    """Fused softmax-CE (mean over rows). NOTE: consumes ``logits`` (overwritten by d loss/d logits).
+
+    ``unit_grad=True`` assumes the loss is the root of backward (upstream gradient == 1)."""
+    return _CrossEntropy.apply(logits, targets, v_real or logits.shape[-1], ignore_index, unit_grad)
+
+
+class _Embedding(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, wte, wpe):
+        B, T = idx.shape
+        C = wte.shape[1]
+        out = torch.empty((B, T, C), dtype=torch.bfloat16, device=wte.device)
+        rc = _lib.cuda().mg_embed_fwd(idx.data_ptr(), wte.data_ptr(), wpe.data_ptr(), out.data_ptr(),
+                                      B * T, T, C, _stream())
+        _lib.check(rc, "mg_embed_fwd")
+        _count(1)
+        ctx.save_for_backward(idx)
+        ctx.refs = (wte, wpe)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        wte, wpe = ctx.refs
+        B, T = idx.shape
+        C = wte.shape[1]
+        dout = dout.contiguous()
+        use_main = getattr(wte, "main_grad", None) is not None
+        if use_main:
+            dwte, dwpe = wte.main_grad, wpe.main_grad
+            if not getattr(wte, "_mg_written", False):
+                dwte.zero_()
+            acc_wpe = bool(getattr(wpe, "_mg_written", False))
+            if not acc_wpe and T < wpe.shape[0]:
+                dwpe[T:].zero_()
+            wte._mg_written = wpe._mg_written = True
+        else:
+            dwte = torch.zeros_like(wte)
+            dwpe = torch.zeros_like(wpe) if T < wpe.shape[0] else torch.empty_like(wpe)
+            acc_wpe = False
+        rc = _lib.cuda().mg_embed_bwd(idx.data_ptr(), dout.data_ptr(), dwte.data_ptr(), dwpe.data_ptr(),
+                                      B, T, C, 1 if acc_wpe else 0, _stream())
+        _lib.check(rc, "mg_embed_bwd")
+        _count(2)
+        if use_main:
+            return None, None, None
+        return None, dwte, dwpe
+
+
+def embedding(idx, wte, wpe):
+    return _Embedding.apply(idx, wte, wpe)

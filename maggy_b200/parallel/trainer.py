@@ -1,0 +1,95 @@
+"""Whole-step execution engine: forward + backward + fused optimizer as ONE replayable CUDA graph.
+
+B200-first replacement for the per-op eager loop the reference leaves to the user inside train_fn
+(maggy/core/executors/torch_dist_executor.py:145-159): the step is launch-bound at small batch on a
+148-SM part, so the engine captures it once (CUDA streams + graphs instead of a tracing compiler)
+and replays it; per-step host work is one pinned H2D copy of the batch and, optionally, one D2H
+read of the loss.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from .arena import FlatParams, FusedAdamW
+
+
+class TrainStep:
+    """``step(idx_host, tgt_host) -> loss`` (device scalar). Inputs may be pinned host or device tensors."""
+
+    def __init__(self, model: torch.nn.Module, optimizer: FusedAdamW, batch_shape, device,
+                 use_cuda_graph: bool = True, warmup_iters: int = 3, input_dtype=torch.long,
+                 loss_fn: Optional[Callable] = None):
+        self.model, self.opt = model, optimizer
+        self.device = torch.device(device)
+        self.idx = torch.zeros(batch_shape, dtype=input_dtype, device=self.device)
+        self.tgt = torch.zeros(batch_shape, dtype=torch.long, device=self.device)
+        self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        self.loss_fn = loss_fn
+        self.graph = None
+        self.use_cuda_graph = use_cuda_graph
+        self.warmup_iters = warmup_iters
+        self.kernels_per_step = 0
+        self._captured = False
+
+    def _eager(self):
+        self.opt.zero_grad()
+        if self.loss_fn is not None:
+            loss = self.loss_fn(self.model, self.idx, self.tgt)
+        else:
+            loss = self.model(self.idx, self.tgt)
+        loss.backward()
+        self.opt.step()
+        self.loss.copy_(loss.detach())
+
+    def _capture(self):
+        from ..ops import functional as F
+
+        self.opt.graph_safe = True
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(self.warmup_iters):
+                self._eager()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        before = F.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._eager()
+        self.kernels_per_step = F.launch_count() - before
+        self._captured = True
+
+    def load_batch(self, idx, tgt):
+        self.idx.copy_(idx, non_blocking=True)
+        self.tgt.copy_(tgt, non_blocking=True)
+
+    def __call__(self, idx=None, tgt=None) -> torch.Tensor:
+        if idx is not None:
+            self.load_batch(idx, tgt)
+        if self.use_cuda_graph:
+            if not self._captured:
+                self._capture()
+            self.graph.replay()
+        else:
+            from ..ops import functional as F
+
+            before = F.launch_count()
+            self._eager()
+            self.kernels_per_step = F.launch_count() - before
+        return self.loss
+
+
+def build_gpt2_trainer(cfg, batch_size: int, seq_len: int, device, world_size: int = 1, rank: int = 0,
+                       group=None, lr: float = 3e-4, weight_decay: float = 0.1, use_cuda_graph: bool = True,
+                       use_multicast: bool = True, seed: int = 1234):
+    """Public convenience constructor used by bench.py / smoke(): GPT-2 + arena + fused AdamW + graph."""
+    from ..models.gpt2 import GPT2
+
+    torch.manual_seed(seed)
+    model = GPT2(cfg)
+    flat = FlatParams(model, device=device, world_size=world_size, rank=rank, group=group)
+    opt = FusedAdamW(flat, lr=lr, weight_decay=weight_decay, use_multicast=use_multicast)
+    step = TrainStep(model, opt, (batch_size, seq_len), device, use_cuda_graph=use_cuda_graph)
+    return model, flat, opt, step
