@@ -1,0 +1,325 @@
+"""Control-plane endpoints over the shared-memory rings (replaces reference maggy/core/rpc.py).
+
+The reference's ``Server``/``Client`` pair speaks length-prefixed cloudpickle over TCP with a 1 s
+heartbeat and a 1 s GET poll (maggy/core/rpc.py:205-257, 716-748). Here both ends are thin ctypes
+wrappers over ``libmaggy_b200_host.so`` (csrc/ctrl/ring.cpp):
+
+========================  =====================================================================
+reference message         here
+========================  =====================================================================
+REG                       ``WorkerChannel.register`` -> REG record
+METRIC (heartbeat)        ``WorkerChannel.post_metric`` (host) / ``post_metric_device`` (GPU kernel K8)
+STOP (heartbeat reply)    per-worker stop word, written by the native policy engine / K9 / driver
+FINAL                     ``WorkerChannel.post_final`` -> FINAL record + pickled blob
+GET / TRIAL               ``DriverChannel.assign`` writes the slot; ``WorkerChannel.wait_assign`` futex-waits
+GSTOP                     ``DriverChannel.gstop``
+LOG                       ``WorkerChannel.post_log`` -> LOG record + text blob
+BLACK                     ``DriverChannel.dead_workers`` (heartbeat timeout) + re-REG with attempt > 0
+QUERY / EXEC_CONFIG       not needed: rendezvous facts travel in the assign payload of gang trials
+secret (auth)             the segment is created 0600 under a random name; only same-user processes
+                          that were handed the name can attach
+========================  =====================================================================
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import secrets
+import time
+from typing import List, Optional
+
+import cloudpickle
+
+from ..ops import _lib
+
+REC_REG, REC_METRIC, REC_FINAL, REC_LOG, REC_IDLE, REC_ERROR, REC_HEARTBEAT, REC_EXIT = 1, 2, 3, 4, 5, 6, 7, 8
+REC_NAMES = {1: "REG", 2: "METRIC", 3: "FINAL", 4: "LOG", 5: "IDLE", 6: "ERROR", 7: "HEARTBEAT", 8: "EXIT"}
+W_EMPTY, W_REGISTERED, W_IDLE, W_RUNNING, W_DONE, W_DEAD = 0, 1, 2, 3, 4, 5
+
+
+class MgRecord(ctypes.Structure):
+    _fields_ = [("seq", ctypes.c_uint64), ("type", ctypes.c_uint16), ("worker", ctypes.c_uint16),
+                ("aux", ctypes.c_uint32), ("trial_id", ctypes.c_uint64), ("step", ctypes.c_int64),
+                ("value", ctypes.c_double), ("t_ns", ctypes.c_uint64), ("reserved", ctypes.c_uint64 * 2)]
+
+
+assert ctypes.sizeof(MgRecord) == 64
+
+_configured = False
+
+
+def _host():
+    global _configured
+    lib = _lib.host()
+    if _configured:
+        return lib
+    P, u32, u64, i64, i32, dbl = (ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int64,
+                                  ctypes.c_int, ctypes.c_double)
+
+    def sig(name, argtypes, restype=i32):
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = argtypes, restype
+
+    sig("mgr_create", [ctypes.c_char_p, u32, u32, u32], P)
+    sig("mgr_attach", [ctypes.c_char_p], P)
+    sig("mgr_close", [P, i32], None)
+    sig("mgr_base", [P], P)
+    sig("mgr_bytes", [P], u64)
+    sig("mgr_num_workers", [P], u32)
+    sig("mgr_now_ns", [], u64)
+    sig("mgr_off_dev_ring", [P, u32], u64)
+    sig("mgr_off_ctl", [P, u32], u64)
+    sig("mgr_ring_slots", [P], u32)
+    sig("mgr_post", [P, u32, u32, u64, i64, dbl, u32])
+    sig("mgr_post_blob", [P, u32, u32, u64, i64, dbl, ctypes.c_char_p, u32, i64])
+    sig("mgr_register", [P, u32, u32, u32])
+    sig("mgr_set_state", [P, u32, u32], None)
+    sig("mgr_heartbeat", [P, u32], None)
+    sig("mgr_wait_assign", [P, u32, i64, ctypes.POINTER(u64), P, u32, ctypes.POINTER(u32)])
+    sig("mgr_check_stop", [P, u32, u64])
+    sig("mgr_gstop_set", [P])
+    sig("mgr_assign", [P, u32, u64, ctypes.c_char_p, u32])
+    sig("mgr_stop_trial", [P, u32, u64], None)
+    sig("mgr_gstop", [P], None)
+    sig("mgr_read_blob", [P, u32, P, u32])
+    sig("mgr_worker_heartbeat", [P, u32], u64)
+    sig("mgr_worker_state", [P, u32], u32)
+    sig("mgr_worker_pid", [P, u32], u32)
+    sig("mgr_dev_dropped", [P, u32], u64)
+    sig("mgr_stop_time_ns", [P, u32], u64)
+    sig("mgr_policy_config", [P, u32, i32, u32, u32], None)
+    sig("mgr_policy_stops", [P], u64)
+    sig("mgr_start_pump", [P], None)
+    sig("mgr_stop_pump", [P], None)
+    sig("mgr_next", [P, ctypes.POINTER(MgRecord), i32, i64])
+    sig("mgr_poll", [P, ctypes.POINTER(MgRecord), i32])
+    _configured = True
+    return lib
+
+
+def now_ns() -> int:
+    return int(_host().mgr_now_ns())
+
+
+def new_segment_name() -> str:
+    return f"/maggy_b200_{os.getpid()}_{secrets.token_hex(8)}"
+
+
+class DriverChannel:
+    """Driver end: owns the segment, drains records, assigns trials, issues stops."""
+
+    def __init__(self, num_workers: int, ring_slots: int = 1024, payload_bytes: int = 1 << 20,
+                 name: Optional[str] = None, pump: bool = True):
+        self.lib = _host()
+        self.name = name or new_segment_name()
+        self.num_workers = num_workers
+        self.payload_bytes = payload_bytes
+        self.h = self.lib.mgr_create(self.name.encode(), num_workers, ring_slots, payload_bytes)
+        if not self.h:
+            raise OSError(f"could not create control segment {self.name}")
+        self._buf = (MgRecord * 256)()
+        self._blob = ctypes.create_string_buffer(int(self.lib.mgr_bytes(self.h)) and payload_bytes + 4096)
+        self.pump = pump
+        if pump:
+            self.lib.mgr_start_pump(self.h)
+
+    # -- receive ---------------------------------------------------------------------------------
+    def next(self, timeout_s: float = 0.05) -> List[dict]:
+        """Blocking fetch (releases the GIL). Each message is a dict mirroring the reference's RPC
+        messages: ``{"type", "partition_id", "trial_id", "data", "step", "t_ns", "stopped"}``;
+        FINAL/LOG carry the unpickled blob in ``data``."""
+        if self.pump:
+            n = self.lib.mgr_next(self.h, self._buf, 256, int(timeout_s * 1e6))
+        else:
+            n = self.lib.mgr_poll(self.h, self._buf, 256)
+            if n == 0 and timeout_s > 0:
+                time.sleep(min(timeout_s, 0.0005))
+        out = []
+        for i in range(n):
+            r = self._buf[i]
+            msg = {"type": REC_NAMES.get(r.type, "ERR"), "partition_id": int(r.worker),
+                   "trial_id": f"{r.trial_id:016x}" if r.trial_id else None, "step": int(r.step),
+                   "value": float(r.value), "t_ns": int(r.t_ns), "aux": int(r.aux),
+                   "stopped": bool(r.reserved[0]), "data": None}
+            if r.type in (REC_FINAL, REC_LOG, REC_ERROR) and r.aux > 0:
+                k = self.lib.mgr_read_blob(self.h, r.worker, self._blob, len(self._blob))
+                if k > 0:
+                    raw = self._blob.raw[:k]
+                    msg["data"] = raw.decode("utf-8", "replace") if r.type == REC_LOG else cloudpickle.loads(raw)
+            out.append(msg)
+        return out
+
+    # -- send ------------------------------------------------------------------------------------
+    def assign(self, worker: int, trial_id: str, payload) -> bool:
+        """Place a trial in the worker's assign slot. False if the previous one was not picked up yet."""
+        blob = cloudpickle.dumps(payload)
+        if len(blob) > self.payload_bytes:
+            raise ValueError(f"trial payload of {len(blob)} bytes exceeds the {self.payload_bytes}-byte assign slot")
+        rc = self.lib.mgr_assign(self.h, worker, int(trial_id, 16), blob, len(blob))
+        if rc == -2:
+            return False
+        if rc != 0:
+            raise OSError(f"mgr_assign failed: {rc}")
+        return True
+
+    def stop_trial(self, worker: int, trial_id: str):
+        self.lib.mgr_stop_trial(self.h, worker, int(trial_id, 16))
+
+    def gstop(self):
+        self.lib.mgr_gstop(self.h)
+
+    def configure_policy(self, enabled: bool, direction: str, es_min: int, es_interval: int):
+        """Arm the native median-stopping-rule engine (csrc/ctrl/ring.cpp policy_on_metric)."""
+        self.lib.mgr_policy_config(self.h, 1 if enabled else 0, 1 if direction == "max" else -1, es_min,
+                                   max(1, es_interval))
+
+    # -- liveness --------------------------------------------------------------------------------
+    def heartbeat_age_s(self, worker: int) -> float:
+        hb = int(self.lib.mgr_worker_heartbeat(self.h, worker))
+        return float("inf") if hb == 0 else (now_ns() - hb) / 1e9
+
+    def worker_state(self, worker: int) -> int:
+        return int(self.lib.mgr_worker_state(self.h, worker))
+
+    def worker_pid(self, worker: int) -> int:
+        return int(self.lib.mgr_worker_pid(self.h, worker))
+
+    def policy_stops(self) -> int:
+        return int(self.lib.mgr_policy_stops(self.h))
+
+    def stop_time_ns(self, worker: int) -> int:
+        return int(self.lib.mgr_stop_time_ns(self.h, worker))
+
+    def close(self, unlink: bool = True):
+        if self.h:
+            self.lib.mgr_close(self.h, 1 if unlink else 0)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class WorkerChannel:
+    """Worker end (one per worker process)."""
+
+    GSTOP = object()
+
+    def __init__(self, name: str, worker_id: int, attempt: int = 0):
+        self.lib = _host()
+        self.name, self.worker, self.attempt = name, worker_id, attempt
+        self.h = None
+        deadline = time.time() + 30
+        while not self.h:
+            self.h = self.lib.mgr_attach(name.encode())
+            if not self.h:
+                if time.time() > deadline:
+                    raise OSError(f"could not attach control segment {name}")
+                time.sleep(0.01)
+        self._payload = ctypes.create_string_buffer(1 << 20)
+        self._dev = None  # lazily created device-side producer state
+
+    def register(self):
+        rc = self.lib.mgr_register(self.h, self.worker, self.attempt, os.getpid())
+        if rc != 0:
+            raise OSError(f"mgr_register failed: {rc}")
+
+    def set_state(self, state: int):
+        self.lib.mgr_set_state(self.h, self.worker, state)
+
+    def heartbeat(self):
+        self.lib.mgr_heartbeat(self.h, self.worker)
+
+    def post_metric(self, trial_id: str, value: float, step: int):
+        self.lib.mgr_post(self.h, self.worker, REC_METRIC, int(trial_id, 16), int(step), float(value), 0)
+
+    def post_idle(self):
+        self.lib.mgr_post(self.h, self.worker, REC_IDLE, 0, 0, 0.0, 0)
+
+    def post_exit(self):
+        self.lib.mgr_post(self.h, self.worker, REC_EXIT, 0, 0, 0.0, 0)
+
+    def _post_blob(self, rec_type, trial_id, step, value, blob: bytes):
+        rc = self.lib.mgr_post_blob(self.h, self.worker, rec_type, int(trial_id, 16) if trial_id else 0, int(step),
+                                    float(value), blob, len(blob), 30_000_000)
+        if rc != 0:
+            raise OSError(f"mgr_post_blob failed: {rc}")
+
+    def post_final(self, trial_id: str, metric, payload: Optional[dict] = None, step: int = 0):
+        data = {"metric": metric}
+        if payload:
+            data.update(payload)
+        v = float(metric) if isinstance(metric, (int, float)) else float("nan")
+        self._post_blob(REC_FINAL, trial_id, step, v, cloudpickle.dumps(data))
+
+    def post_error(self, trial_id: Optional[str], text: str):
+        self._post_blob(REC_ERROR, trial_id, 0, float("nan"), cloudpickle.dumps({"error": text}))
+
+    def post_log(self, trial_id: Optional[str], text: str):
+        if text:
+            self._post_blob(REC_LOG, trial_id, 0, 0.0, text.encode("utf-8")[-(1 << 19):])
+
+    def wait_assign(self, timeout_s: float = 1.0):
+        """-> (trial_id, payload) | None (timeout) | WorkerChannel.GSTOP."""
+        tid, n = ctypes.c_uint64(0), ctypes.c_uint32(0)
+        rc = self.lib.mgr_wait_assign(self.h, self.worker, int(timeout_s * 1e6), ctypes.byref(tid), self._payload,
+                                      len(self._payload), ctypes.byref(n))
+        if rc == 1:
+            payload = cloudpickle.loads(self._payload.raw[:n.value]) if n.value else None
+            return f"{tid.value:016x}", payload
+        if rc == 2:
+            return WorkerChannel.GSTOP
+        if rc == 0:
+            return None
+        raise OSError(f"mgr_wait_assign failed: {rc}")
+
+    def check_stop(self, trial_id: str) -> bool:
+        return bool(self.lib.mgr_check_stop(self.h, self.worker, int(trial_id, 16)))
+
+    def gstop_set(self) -> bool:
+        return bool(self.lib.mgr_gstop_set(self.h))
+
+    # -- device path (K8) ------------------------------------------------------------------------
+    def _device_state(self):
+        if self._dev is None:
+            import torch
+
+            cu = _lib.cuda()
+            u64, P = ctypes.c_ulonglong, ctypes.c_void_p
+            cu.mg_ring_map.argtypes, cu.mg_ring_map.restype = [P, u64], u64
+            cu.mg_report_store.argtypes = [u64, u64, u64, ctypes.c_uint, P, ctypes.c_int, ctypes.c_longlong, u64,
+                                           ctypes.c_uint, P, P]
+            cu.mg_report_store.restype = ctypes.c_int
+            base = self.lib.mgr_base(self.h)
+            dev_base = cu.mg_ring_map(base, self.lib.mgr_bytes(self.h))
+            if not dev_base:
+                raise RuntimeError("cudaHostRegister of the control segment failed")
+            self._dev = {
+                "cu": cu, "base": dev_base,
+                "off_ring": int(self.lib.mgr_off_dev_ring(self.h, self.worker)),
+                "off_ctl": int(self.lib.mgr_off_ctl(self.h, self.worker)),
+                "slots": int(self.lib.mgr_ring_slots(self.h)),
+                "state": torch.zeros(8, dtype=torch.int32, device="cuda"),
+            }
+        return self._dev
+
+    def post_metric_device(self, trial_id: str, tensor, step: int):
+        """Publish a 0-dim CUDA tensor as a METRIC record from the GPU (no host synchronisation)."""
+        import torch
+
+        d = self._device_state()
+        code = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2, torch.float64: 3}.get(tensor.dtype)
+        if code is None:
+            tensor, code = tensor.float(), 0
+        rc = d["cu"].mg_report_store(d["base"], d["off_ring"], d["off_ctl"], d["slots"], tensor.data_ptr(), code,
+                                     int(step), int(trial_id, 16), self.worker, d["state"].data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"mg_report_store failed: {rc}")
+
+    def close(self):
+        if self.h:
+            self.lib.mgr_close(self.h, 0)
+            self.h = None
