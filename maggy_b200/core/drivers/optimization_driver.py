@@ -1,0 +1,449 @@
+"""Hyperparameter-optimization driver (reference: maggy/core/experiment_driver/optimization_driver.py:40-691).
+
+Keeps the reference's bookkeeping (trial stores, result aggregation, ``trial.json`` / ``result.json`` /
+``maggy.json`` artefacts, progress lines) and message semantics (REG / METRIC / FINAL / IDLE / BLACK), on
+top of the ring control plane:
+
+* a finishing worker gets its next trial in the same digest turn as its FINAL (no 1 s GET poll);
+* the median stopping rule is armed in the native policy engine, which writes the STOP word itself;
+  the Python driver only mirrors the decision into the Trial (custom ``AbstractEarlyStop`` policies
+  still run here and stop trials through ``channel.stop_trial``);
+* model-based controllers get a one-deep lookahead: the next suggestion is computed on a helper thread
+  while trials run, so a GP/TPE fit never sits between FINAL and the next assignment.
+"""
+from __future__ import annotations
+
+import json
+import os
+import threading
+import time
+from typing import Optional
+
+from ... import tensorboard, util
+from ...earlystop import AbstractEarlyStop, MedianStoppingRule, NoStoppingRule
+from ...optimizer import AbstractOptimizer, Asha, GridSearch, RandomSearch, SingleRun
+from ...optimizer.bayes import GP, TPE
+from ...searchspace import Searchspace
+from ...trial import Trial
+from ..environment.singleton import EnvSing
+from .base import Driver
+
+
+class HyperparameterOptDriver(Driver):
+    controller_dict = {
+        "randomsearch": RandomSearch,
+        "asha": Asha,
+        "tpe": TPE,
+        "gp": GP,
+        "none": SingleRun,
+        "faulty_none": None,
+        "gridsearch": GridSearch,
+    }
+    executor_kind = "trial"
+    experiment_type = "optimization"
+
+    def __init__(self, config, app_id, run_id):
+        super().__init__(config, app_id, run_id)
+        self._final_store = []
+        self._trial_store = {}
+        self._store_lock = threading.RLock()
+        self.experiment_done = False
+        self.maggy_log = ""
+        self.job_end = None
+        self.duration = None
+        self.searchspace = self._init_searchspace(config.searchspace)
+        self.controller = self._init_controller(config.optimizer, self.searchspace)
+        self.optimization_key = getattr(config, "optimization_key", "Metric")
+        self.direction = self._init_direction(config.direction)
+        self.num_trials = config.num_trials
+        if self.controller.pruner:
+            self.num_trials = self.controller.pruner.num_trials()
+        if isinstance(self.controller, GridSearch):
+            self.num_trials = self.controller.get_num_trials(self.searchspace)
+        self.gpus_per_worker = max(1, int(getattr(config, "gpus_per_trial", 1) or 1))
+        wanted = getattr(config, "num_workers", None)
+        pool = wanted or max(1, util.num_executors(default=2) // self.gpus_per_worker)
+        self.num_executors = max(1, min(pool, self.num_trials))
+        self.earlystop_check = self._init_earlystop_check(config.es_policy)
+        self.es_interval = config.es_interval
+        self.es_min = config.es_min
+        self.result = {"best_val": "n.a.", "num_trials": 0, "early_stopped": 0}
+        if getattr(config, "seed", None) is not None:
+            import random
+
+            import numpy as np
+
+            random.seed(config.seed)
+            np.random.seed(config.seed)
+        # shared state of the controller (reference optimization_driver.py:112-117)
+        self.controller.num_trials = self.num_trials
+        self.controller.searchspace = self.searchspace
+        self.controller.trial_store = self._trial_store
+        self.controller.final_store = self._final_store
+        self.controller.direction = self.direction
+        self.controller._initialize(exp_dir=self.log_dir)
+        # scheduling state
+        self._assigned = {}          # worker -> trial_id currently assigned / running
+        self._idle = {}              # worker -> time of the last failed suggestion
+        self._scheduled = 0
+        self._controller_exhausted = False
+        self._lookahead_enabled = isinstance(self.controller, (GP, TPE)) and not self.controller.pruner
+        self._lookahead = None       # a Trial computed ahead of time
+        self._lookahead_thread: Optional[threading.Thread] = None
+        self._controller_lock = threading.RLock()
+        self.inter_trial_gaps = []   # seconds between a FINAL and the next assignment on that worker
+        self.stop_latencies = []     # seconds between the decisive METRIC record and the STOP word
+
+    # ------------------------------------------------------------------ hooks
+    def _exp_startup_callback(self) -> None:
+        try:
+            tensorboard._register(self.log_dir)
+            tensorboard._write_hparams_config(self.log_dir, self.searchspace)
+        except Exception:
+            pass
+
+    def _exp_final_callback(self, job_end: float, exp_json: dict) -> dict:
+        result = self.finalize(job_end)
+        best_logdir = os.path.join(self.log_dir, str(result.get("best_id")))
+        util.finalize_experiment(exp_json, float(result["best_val"]) if result.get("best_id") else None, self.app_id,
+                                 self.run_id, "FINISHED", self.duration, self.log_dir, best_logdir,
+                                 self.optimization_key)
+        print("Finished experiment.")
+        return result
+
+    def _exp_exception_callback(self, exc: Exception) -> None:
+        self.log(f"Experiment failed: {exc!r}")
+
+    def _register_msg_callbacks(self) -> None:
+        self.message_callbacks.update({
+            "REG": self._register_msg_callback, "METRIC": self._metric_msg_callback,
+            "FINAL": self._final_msg_callback, "LOG": self._log_msg_callback,
+            "ERROR": self._error_msg_callback, "IDLE": lambda msg: None, "EXIT": lambda msg: None,
+        })
+
+    def init(self, job_start: float) -> None:
+        super().init(job_start)
+        native_median = isinstance(self.earlystop_check, type) and issubclass(self.earlystop_check, MedianStoppingRule) \
+            or isinstance(self.earlystop_check, MedianStoppingRule)
+        self._native_policy = bool(native_median)
+        self.channel.configure_policy(self._native_policy, self.direction, self.es_min, self.es_interval)
+
+    def _picklable_config(self, config):
+        # the controller / searchspace objects stay on the driver; workers only need these fields
+        class _Slim:
+            pass
+
+        slim = _Slim()
+        for k in ("name", "description", "hb_interval", "model", "dataset", "optimization_key"):
+            setattr(slim, k, getattr(config, k, None))
+        slim.optimization_key = self.optimization_key
+        return slim
+
+    # ------------------------------------------------------------------ controller access
+    def controller_get_next(self, trial=None):
+        return self.controller.get_suggestion(trial)
+
+    def _suggest(self, finished_trial=None):
+        """Next Trial | "IDLE" | None. Uses the lookahead buffer when it holds something."""
+        if self._lookahead_enabled:
+            t = self._lookahead_thread
+            if t is not None and not t.is_alive():
+                self._lookahead_thread = None
+            if self._lookahead is not None:
+                nxt, self._lookahead = self._lookahead, None
+                return nxt
+            if self._lookahead_thread is not None:
+                self._lookahead_thread.join()
+                self._lookahead_thread = None
+                if self._lookahead is not None:
+                    nxt, self._lookahead = self._lookahead, None
+                    return nxt
+        with self._controller_lock:
+            return self.controller_get_next(finished_trial)
+
+    def _kick_lookahead(self, finished_trial):
+        if not self._lookahead_enabled or self._lookahead is not None or self._lookahead_thread is not None:
+            return
+        if self._controller_exhausted or self._scheduled + 1 >= self.num_trials + len(self._idle):
+            return
+
+        def work():
+            try:
+                with self._controller_lock:
+                    nxt = self.controller_get_next(finished_trial)
+                if isinstance(nxt, Trial):
+                    self._lookahead = nxt
+            except Exception as exc:  # noqa: BLE001
+                self.exception = exc
+
+        self._lookahead_thread = threading.Thread(target=work, name="maggy-suggest", daemon=True)
+        self._lookahead_thread.start()
+
+    # ------------------------------------------------------------------ scheduling
+    def _assign_next(self, worker: int, finished_trial=None, t_final=None):
+        if self.experiment_done:
+            return
+        if self._controller_exhausted:
+            self._maybe_finish()
+            return
+        nxt = self._suggest(finished_trial)
+        if nxt is None:
+            self._controller_exhausted = True
+            self._idle.pop(worker, None)
+            self._maybe_finish()
+            return
+        if nxt == "IDLE":
+            self._idle[worker] = (time.time(), finished_trial)
+            return
+        self._idle.pop(worker, None)
+        self._schedule(worker, nxt)
+        if t_final is not None:
+            self.inter_trial_gaps.append(time.time() - t_final)
+        self._kick_lookahead(finished_trial)
+
+    def _schedule(self, worker: int, trial: Trial):
+        with self._store_lock:
+            if trial.trial_id in self._trial_store:
+                self.log(f"WARNING trial {trial.trial_id} is already running; asking the controller again")
+            self._trial_store[trial.trial_id] = trial
+        trial.status = Trial.SCHEDULED
+        trial.start = time.time()
+        payload = {"params": trial.params, "trial_type": trial.trial_type}
+        while not self.channel.assign(worker, trial.trial_id, payload):
+            time.sleep(0.0005)  # the worker has not picked up its previous assignment yet
+        trial.status = Trial.RUNNING
+        self._assigned[worker] = trial.trial_id
+        self._scheduled += 1
+
+    def _maybe_finish(self):
+        if not self._assigned and (self._controller_exhausted or len(self._final_store) >= self.num_trials):
+            self.experiment_done = True
+
+    def _on_tick(self) -> None:
+        if not self._idle or self.experiment_done:
+            return
+        now = time.time()
+        for worker, (since, last) in list(self._idle.items()):
+            if now - since >= 0.05:  # reference retries every 0.1 s (optimization_driver.py:550)
+                self._assign_next(worker, last)
+
+    # ------------------------------------------------------------------ message callbacks
+    def _register_msg_callback(self, msg) -> None:
+        worker = msg["partition_id"]
+        lost = self._assigned.get(worker)
+        if lost is not None:
+            # a restarted worker re-registers while a trial is still assigned to it: the reference marks the
+            # trial ERROR and re-schedules the very same trial on this partition (BLACK, rpc.py:421-432)
+            trial = self.get_trial(lost)
+            if trial is not None:
+                trial.status = Trial.ERROR
+                self.log(f"worker {worker} re-registered (attempt {msg['aux']}): rescheduling lost trial {lost}")
+                trial.metric_history, trial.step_history, trial.metric_dict = [], [], {}
+                trial.early_stop = False
+                self._scheduled -= 1
+                self._schedule(worker, trial)
+                return
+        self._assign_next(worker, None)
+
+    def _metric_msg_callback(self, msg) -> None:
+        trial = self.get_trial(msg["trial_id"])
+        if trial is None:
+            return
+        new_step = trial.append_metric({"value": msg["value"], "step": msg["step"]})
+        if msg["stopped"]:
+            trial.set_early_stop()
+            self.stop_latencies.append(max(0.0, (self.channel.stop_time_ns(msg["partition_id"]) - msg["t_ns"]) / 1e9))
+            return
+        if self._native_policy or new_step is None or trial.get_early_stop():
+            return
+        with self._store_lock:
+            finals = list(self._final_store)
+        if len(finals) > self.es_min and new_step % self.es_interval == 0:
+            try:
+                to_stop = self.earlystop_check(trial, finals, self.direction)
+            except Exception as e:  # noqa: BLE001
+                self.log(str(e))
+                to_stop = None
+            if to_stop is not None:
+                self.log(f"Trials to stop: {to_stop}")
+                trial.set_early_stop()
+                self.channel.stop_trial(msg["partition_id"], trial.trial_id)
+
+    def _log_msg_callback(self, msg) -> None:
+        if msg["data"]:
+            self.add_executor_logs(msg["data"])
+
+    def _error_msg_callback(self, msg) -> None:
+        text = (msg["data"] or {}).get("error", "unknown error") if isinstance(msg["data"], dict) else str(msg["data"])
+        trial = self.get_trial(msg["trial_id"]) if msg["trial_id"] else None
+        if trial is not None:
+            trial.status = Trial.ERROR
+        self.log(f"worker {msg['partition_id']} failed in trial {msg['trial_id']}:\n{text}")
+        self.exception = RuntimeError(
+            f"train_fn raised in trial {msg['trial_id']} on worker {msg['partition_id']}:\n{text}")
+
+    def _final_msg_callback(self, msg) -> None:
+        t_final = time.time()
+        worker = msg["partition_id"]
+        trial = self.get_trial(msg["trial_id"])
+        data = msg["data"] or {}
+        if trial is None:
+            return
+        if data.get("logs"):
+            self.add_executor_logs(data["logs"])
+        with self._controller_lock, self._store_lock:
+            trial.status = Trial.FINALIZED
+            trial.final_metric = data.get("metric", msg["value"])
+            trial.duration = util.seconds_to_milliseconds(time.time() - trial.start)
+            self._final_store.append(trial)
+            self._trial_store.pop(trial.trial_id, None)
+        self._assigned.pop(worker, None)
+        # hand the worker its next trial first, do the bookkeeping while it is already training
+        self._assign_next(worker, trial, t_final)
+        self._update_result(trial)
+        self.maggy_log = self._update_maggy_log()
+        self.log(self.maggy_log)
+        EnvSing.get_instance().dump(trial.to_json(), os.path.join(self.log_dir, trial.trial_id, "trial.json"))
+        self._maybe_finish()
+
+    # ------------------------------------------------------------------ stores
+    def get_trial(self, trial_id):
+        with self._store_lock:
+            return self._trial_store.get(trial_id)
+
+    def add_trial(self, trial):
+        with self._store_lock:
+            self._trial_store[trial.trial_id] = trial
+
+    # ------------------------------------------------------------------ results / artefacts
+    def _update_result(self, trial: Trial) -> None:
+        metric = trial.final_metric
+        params = {k: v for k, v in trial.params.items() if k not in ("dataset_function", "model_function")}
+        r = self.result
+        if r.get("best_id") is None:
+            self.result = {"best_id": trial.trial_id, "best_val": metric, "best_config": params,
+                           "worst_id": trial.trial_id, "worst_val": metric, "worst_config": params, "avg": metric,
+                           "metric_list": [metric], "num_trials": 1, "early_stopped": 1 if trial.early_stop else 0,
+                           "num_epochs": len(trial.metric_history), "trial_id": trial.trial_id}
+            return
+        better = (lambda a, b: a > b) if self.direction == "max" else (lambda a, b: a < b)
+        if better(metric, r["best_val"]):
+            r.update(best_val=metric, best_id=trial.trial_id, best_config=params)
+        if better(r["worst_val"], metric):
+            r.update(worst_val=metric, worst_id=trial.trial_id, worst_config=params)
+        r["metric_list"].append(metric)
+        r["num_trials"] += 1
+        r["avg"] = sum(r["metric_list"]) / float(len(r["metric_list"]))
+        if trial.early_stop:
+            r["early_stopped"] += 1
+
+    def finalize(self, job_end: float) -> dict:
+        self.job_end = job_end
+        self.duration = util.seconds_to_milliseconds(job_end - self.job_start)
+        results = self.prep_results(util.time_diff(self.job_start, job_end))
+        print(results)
+        self.log(results)
+        env = EnvSing.get_instance()
+        env.dump(json.dumps(self.result, default=util.json_default_numpy), os.path.join(self.log_dir, "result.json"))
+        env.dump(self.json(), os.path.join(self.log_dir, "maggy.json"))
+        return self.result
+
+    def prep_results(self, duration_str: str) -> str:
+        self.controller._finalize_experiment(self._final_store)
+        r = self.result
+        return ("\n------ " + self.controller.name() + " Results ------ direction(" + self.direction + ") \n"
+                "BEST combination " + json.dumps(r.get("best_config"), default=util.json_default_numpy)
+                + " -- metric " + str(r.get("best_val")) + "\n"
+                "WORST combination " + json.dumps(r.get("worst_config"), default=util.json_default_numpy)
+                + " -- metric " + str(r.get("worst_val")) + "\n"
+                "AVERAGE metric -- " + str(r.get("avg")) + "\n"
+                "EARLY STOPPED Trials -- " + str(r.get("early_stopped")) + "\n"
+                "Total job time " + duration_str + "\n")
+
+    def config_to_dict(self) -> dict:
+        return self.searchspace.to_dict()
+
+    def json(self) -> str:
+        env = EnvSing.get_instance()
+        exp = {
+            "project": env.project_name(), "user": env.get_user() or None, "name": self.name, "module": "maggy",
+            "app_id": str(self.app_id),
+            "start": time.strftime("%Y-%m-%dT%H:%M:%S", time.localtime(self.job_start)),
+            "memory_per_executor": str(os.environ.get("MAGGY_EXECUTOR_MEMORY")),
+            "gpus_per_executor": str(self.gpus_per_worker if util.num_physical_devices() else 0),
+            "executors": self.num_executors, "logdir": self.log_dir, "description": self.description,
+            "experiment_type": self.controller.name(), "controller": self.controller.name(),
+            "config": json.dumps(self.config_to_dict(), default=util.json_default_numpy),
+        }
+        if self.experiment_done:
+            exp["status"] = "FINISHED"
+            exp["finished"] = time.strftime("%Y-%m-%dT%H:%M:%S", time.localtime(self.job_end))
+            exp["duration"] = self.duration
+            exp["config"] = json.dumps(self.result.get("best_config"), default=util.json_default_numpy)
+            exp["metric"] = self.result.get("best_val")
+        else:
+            exp["status"] = "RUNNING"
+        return json.dumps(exp, default=util.json_default_numpy)
+
+    def _update_maggy_log(self) -> str:
+        return self.log_string()
+
+    def log_string(self) -> str:
+        r = self.result
+        return ("Maggy Optimization " + str(r["num_trials"]) + "/" + str(self.num_trials) + " ("
+                + str(r["early_stopped"]) + ") " + util.progress_bar(r["num_trials"], self.num_trials)
+                + " - BEST " + json.dumps(r.get("best_config"), default=util.json_default_numpy)
+                + " - metric " + str(r["best_val"]))
+
+    # ------------------------------------------------------------------ validation of the config
+    @staticmethod
+    def _init_searchspace(searchspace):
+        if searchspace is None:
+            return Searchspace()
+        if not isinstance(searchspace, Searchspace):
+            raise Exception(f"The experiment's search space should be an instance of maggy.Searchspace, but it is "
+                            f"{searchspace} (of type '{type(searchspace).__name__}').")
+        return searchspace
+
+    @staticmethod
+    def _init_direction(direction):
+        if not isinstance(direction, str) or direction.lower() not in ("min", "max"):
+            raise Exception(f"The experiment's direction should be a string (either 'min' or 'max') but it is "
+                            f"{direction} (of type '{type(direction).__name__}').")
+        return direction.lower()
+
+    def _init_controller(self, optimizer, searchspace):
+        if optimizer is None:
+            optimizer = "none"
+        if isinstance(optimizer, str):
+            key = optimizer.lower()
+            if key not in self.controller_dict or self.controller_dict[key] is None:
+                raise Exception(f"Unknown Optimizer. Can't initialize experiment driver. Got '{optimizer}', expected "
+                                f"one of {[k for k, v in self.controller_dict.items() if v]}.")
+            if key == "none" and len(searchspace.names()) > 0:
+                raise Exception("Searchspace has to be empty or None to use without Optimizer.")
+            return self.controller_dict[key]()
+        if isinstance(optimizer, AbstractOptimizer):
+            print(f"Custom Optimizer initialized: {type(optimizer).__name__}")
+            return optimizer
+        raise Exception(f"The experiment's optimizer should either be an string indicating the name of an implemented "
+                        f"optimizer (such as 'randomsearch') or an instance of maggy.optimizer.AbstractOptimizer, but it "
+                        f"is {optimizer} (of type '{type(optimizer).__name__}').")
+
+    @staticmethod
+    def _init_earlystop_check(es_policy):
+        if isinstance(es_policy, str):
+            key = es_policy.lower()
+            if key == "median":
+                return MedianStoppingRule.earlystop_check if False else MedianStoppingRule
+            if key == "none":
+                return NoStoppingRule
+            raise Exception(f"The experiment's early stopping policy should either be a string ('median' or 'none') or "
+                            f"a custom policy that is an instance of maggy.earlystop.AbstractEarlyStop, but it is "
+                            f"{es_policy} (of type '{type(es_policy).__name__}').")
+        if isinstance(es_policy, AbstractEarlyStop) or (isinstance(es_policy, type) and issubclass(es_policy, AbstractEarlyStop)):
+            print(f"Custom Early Stopping policy initialized: {getattr(es_policy, '__name__', type(es_policy).__name__)}")
+            return es_policy
+        raise Exception(f"The experiment's early stopping policy should either be a string ('median' or 'none') or a "
+                        f"custom policy that is an instance of maggy.earlystop.AbstractEarlyStop, but it is {es_policy} "
+                        f"(of type '{type(es_policy).__name__}').")

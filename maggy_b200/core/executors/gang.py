@@ -1,0 +1,55 @@
+"""Multi-GPU trial gangs (new capability, BASELINE config 4: "4 trials x 2 GPUs").
+
+The reference runs exactly one process per trial. Here a trial can own ``gpus_per_trial`` GPUs: the
+pool starts that many processes per worker slot; rank 0 (the leader) owns the control ring and the
+others follow it through a gang-private torch.distributed group (NCCL on GPUs, gloo on CPU) that is
+initialised ONCE per worker lifetime, so consecutive trials pay no rendezvous cost. Inside train_fn
+``torch.distributed`` is ready to use (e.g. wrap the model with maggy_b200.parallel.DataParallel).
+"""
+from __future__ import annotations
+
+import datetime
+import os
+
+
+class Gang:
+    def __init__(self, rank: int, size: int, port: int, timeout_s: int = 1800):
+        import torch
+        import torch.distributed as dist
+
+        self.rank, self.size = rank, size
+        os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank),
+                           "WORLD_SIZE": str(size), "LOCAL_RANK": "0"})
+        use_cuda = torch.cuda.is_available()
+        if use_cuda:
+            torch.cuda.set_device(0)  # CUDA_VISIBLE_DEVICES already pins this process to its GPU
+        dist.init_process_group("nccl" if use_cuda else "gloo", rank=rank, world_size=size,
+                                timeout=datetime.timedelta(seconds=timeout_s))
+        self.dist = dist
+        self.device = torch.device("cuda", 0) if use_cuda else torch.device("cpu")
+
+    @property
+    def is_leader(self) -> bool:
+        return self.rank == 0
+
+    def broadcast(self, obj):
+        """Leader -> followers object broadcast (trial assignment, stop sentinel)."""
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=0, device=self.device)
+        return box[0]
+
+    def mean(self, value: float) -> float:
+        import torch
+
+        t = torch.tensor([float(value)], dtype=torch.float64, device=self.device)
+        if self.device.type == "cuda":
+            t = t.float()
+        self.dist.all_reduce(t)
+        return float(t.item()) / self.size
+
+    def close(self):
+        try:
+            if self.dist.is_initialized():
+                self.dist.destroy_process_group()
+        except Exception:
+            pass

@@ -1,0 +1,86 @@
+"""Entry point of every worker process started by the native launcher
+(``python -m maggy_b200.core.executors.worker_main --segment ... --worker-id ... --spec ...``).
+
+Plays the role of the cloudpickled ``executor_fn`` closure the reference ships to Spark tasks
+(maggy/core/experiment_driver/spark_driver.py:136-145): it loads the experiment spec (train_fn,
+config, paths), attaches to the control segment and runs the executor loop selected by the spec.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import traceback
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--segment", required=True)
+    ap.add_argument("--worker-id", type=int, required=True)
+    ap.add_argument("--attempt", type=int, default=0)
+    ap.add_argument("--spec", required=True)
+    ap.add_argument("--gang-rank", type=int, default=0)
+    ap.add_argument("--gang-size", type=int, default=1)
+    ap.add_argument("--gang-port", type=int, default=0)
+    args = ap.parse_args(argv)
+
+    import cloudpickle
+
+    with open(args.spec, "rb") as f:
+        spec = cloudpickle.load(f)
+    for p in spec.get("sys_path", []):
+        if p not in sys.path:
+            sys.path.append(p)
+    os.environ["ML_ID"] = f"{spec['app_id']}_{spec['run_id']}"
+
+    from ..environment.singleton import EnvSing
+    from .. import rpc
+
+    env = EnvSing.get_instance()
+    if spec.get("env_log_dir"):
+        env.log_dir = spec["env_log_dir"]
+
+    gang = None
+    if args.gang_size > 1:
+        from .gang import Gang
+
+        gang = Gang(args.gang_rank, args.gang_size, args.gang_port)
+
+    channel = None
+    if args.gang_rank == 0:
+        channel = rpc.WorkerChannel(args.segment, args.worker_id, attempt=args.attempt)
+    kind = spec["kind"]
+    try:
+        if kind == "trial":
+            from .trial_executor import trial_executor_loop
+
+            trial_executor_loop(spec, channel, args.worker_id, args.attempt, gang)
+        elif kind == "torch_dist":
+            from .torch_dist_executor import torch_dist_executor_loop
+
+            torch_dist_executor_loop(spec, channel, args.worker_id, args.attempt)
+        elif kind == "base":
+            from .base_executor import base_executor_loop
+
+            base_executor_loop(spec, channel, args.worker_id, args.attempt)
+        else:
+            raise ValueError(f"unknown executor kind {kind}")
+    except Exception:
+        text = traceback.format_exc()
+        sys.stderr.write(text)
+        if channel is not None:
+            try:
+                channel.post_error(None, text)
+            except Exception:
+                pass
+        return 1
+    finally:
+        if gang is not None:
+            gang.close()
+        if channel is not None:
+            channel.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

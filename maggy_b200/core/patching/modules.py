@@ -1,0 +1,94 @@
+"""Module class factories for distributed training (reference: maggy/core/patching/modules.py:38-139).
+
+The reference hands train_fn a *class* that, when the user instantiates it, builds the user's module and
+wraps it in DDP / fairscale FSDP / a DeepSpeed engine. Same contract here, different engines:
+
+* ``zero_lvl`` 0-2, module built on maggy_b200 ops (parameters accept the ``main_grad`` convention, e.g.
+  everything in ``maggy_b200.models``): :class:`maggy_b200.parallel.DataParallel` — gradients are reduced
+  by the fused reduce-scatter + Adam + all-gather kernel over NVLink, no DDP buckets;
+* any other ``torch.nn.Module``: stock ``DistributedDataParallel`` (NCCL on GPUs, gloo on CPU) — the
+  library baseline — with ``ZeroRedundancyOptimizer`` for ``zero_lvl`` 1-2 (see patching/optim.py);
+* ``zero_lvl`` 3: ``torch.distributed.fsdp.FullyShardedDataParallel`` with bf16 mixed precision when
+  requested (fairscale / DeepSpeed are not used; ``backend="deepspeed"`` maps its ZeRO stage here).
+"""
+from __future__ import annotations
+
+from typing import Type
+
+import torch
+import torch.distributed as dist
+
+
+def uses_maggy_ops(module: torch.nn.Module) -> bool:
+    """True for modules whose forward runs on maggy_b200 kernels (they declare ``maggy_b200_native``)."""
+    return bool(getattr(module, "maggy_b200_native", False)) or type(module).__module__.startswith("maggy_b200.models")
+
+
+def get_maggy_ddp_wrapper(module: Type[torch.nn.Module]):
+    """Class factory: ``Wrapped(*args, **kw)`` builds ``module(*args, **kw)`` and makes it data parallel."""
+
+    class MaggyDDPModuleWrapper(torch.nn.Module):
+        __module__ = module.__module__
+
+        def __init__(self, *args, **kwargs):
+            super().__init__()
+            model = module(*args, **kwargs)
+            use_cuda = torch.cuda.is_available()
+            if use_cuda and uses_maggy_ops(model):
+                from ...parallel.data_parallel import DataParallel
+
+                self.inner = DataParallel(model)
+                self.fused = True
+            else:
+                from torch.nn.parallel import DistributedDataParallel
+
+                if use_cuda:
+                    model = model.cuda()
+                self.inner = DistributedDataParallel(model) if dist.is_initialized() and dist.get_world_size() > 1 else model
+                self.fused = False
+
+        def forward(self, *args, **kwargs):
+            return self.inner(*args, **kwargs)
+
+    MaggyDDPModuleWrapper.__name__ = f"MaggyDDP_{module.__name__}"
+    return MaggyDDPModuleWrapper
+
+
+def get_maggy_fsdp_wrapper(module: Type[torch.nn.Module], mixed_precision: bool = False):
+    """ZeRO-3: fully sharded parameters / gradients / optimizer state."""
+
+    class MaggyFSDPModuleWrapper(torch.nn.Module):
+        __module__ = module.__module__
+
+        def __init__(self, *args, **kwargs):
+            super().__init__()
+            model = module(*args, **kwargs)
+            if torch.cuda.is_available():
+                model = model.cuda()
+            if dist.is_initialized() and dist.get_world_size() > 1 and torch.cuda.is_available():
+                from torch.distributed.fsdp import FullyShardedDataParallel as FSDP, MixedPrecision
+
+                mp = MixedPrecision(param_dtype=torch.bfloat16, reduce_dtype=torch.float32,
+                                    buffer_dtype=torch.bfloat16) if mixed_precision else None
+                self.inner = FSDP(model, mixed_precision=mp, use_orig_params=True)
+            else:
+                self.inner = model
+
+        def forward(self, *args, **kwargs):
+            return self.inner(*args, **kwargs)
+
+    MaggyFSDPModuleWrapper.__name__ = f"MaggyFSDP_{module.__name__}"
+    return MaggyFSDPModuleWrapper
+
+
+# names used by the reference
+get_maggy_fairscale_wrapper = get_maggy_fsdp_wrapper
+
+
+def get_maggy_deepspeed_wrapper(module: Type[torch.nn.Module], config_params: dict):
+    """DeepSpeed configs are honoured for their ZeRO stage and fp16/bf16 switches only."""
+    stage = int(config_params.get("zero_optimization", {}).get("stage", 0))
+    mixed = bool(config_params.get("fp16", {}).get("enabled") or config_params.get("bf16", {}).get("enabled"))
+    if getattr(module, "__name__", "") == "PipelineModule":
+        raise AssertionError("Maggy does not support pipeline parallelism (reference modules.py:106-109)")
+    return get_maggy_fsdp_wrapper(module, mixed) if stage >= 3 else get_maggy_ddp_wrapper(module)

@@ -1,0 +1,81 @@
+"""ZeRO optimizer patching (reference: maggy/core/patching/optim.py:28-117 and
+torch_dist_executor.py:408-422, which swap ``torch.optim.*`` for ZeRO subclasses process-wide).
+
+Here the swap is *scoped*: ``patched_optimizers(zero_lvl)`` is a context manager active only while
+train_fn runs. Inside it ``torch.optim.Adam`` / ``AdamW`` constructed on the parameters of a fused
+``DataParallel`` module return that module's :class:`~maggy_b200.parallel.FusedAdamW` (reduce-scatter +
+Adam + all-gather in one NVLink kernel); every other optimizer class / module gets
+``ZeroRedundancyOptimizer`` (ZeRO-1) exactly like the reference.
+"""
+from __future__ import annotations
+
+import contextlib
+
+import torch
+import torch.distributed as dist
+
+_ZERO_CLASSES = ["Adadelta", "Adagrad", "Adam", "AdamW", "SparseAdam", "Adamax", "ASGD", "LBFGS", "RMSprop",
+                 "Rprop", "SGD"]
+
+
+def _find_fused_owner(params):
+    """The DataParallel wrapper that owns these parameters (they carry a ``main_grad`` arena view)."""
+    params = list(params)
+    flat = None
+    for p in params:
+        if isinstance(p, dict):
+            return None, params
+        owner = getattr(p, "_maggy_flat", None)
+        if owner is None:
+            return None, params
+        flat = owner
+    return flat, params
+
+
+def make_zero_optimizer(optim_cls):
+    """``MaggyZero<Name>``: same constructor as ``optim_cls``, optimizer state sharded over the ranks."""
+
+    class MaggyZeroOptimizer:
+        def __new__(cls, params, *args, **kwargs):
+            flat, params = _find_fused_owner(params)
+            if flat is not None and optim_cls in (torch.optim.Adam, torch.optim.AdamW):
+                from ...parallel.arena import FusedAdamW
+
+                names = ("lr", "betas", "eps", "weight_decay")
+                kw = dict(zip(names, args))
+                kw.update({k: v for k, v in kwargs.items() if k in names})
+                if optim_cls is torch.optim.Adam:
+                    kw.setdefault("weight_decay", 0.0)
+                return FusedAdamW(flat, **kw)
+            if dist.is_initialized() and dist.get_world_size() > 1:
+                from torch.distributed.optim import ZeroRedundancyOptimizer
+
+                names = list(optim_cls.__init__.__code__.co_varnames[2:optim_cls.__init__.__code__.co_argcount])
+                kw = dict(zip(names, args))
+                kw.update(kwargs)
+                return ZeroRedundancyOptimizer(params, optimizer_class=optim_cls, **kw)
+            return optim_cls(params, *args, **kwargs)
+
+    MaggyZeroOptimizer.__name__ = f"MaggyZero{optim_cls.__name__}"
+    return MaggyZeroOptimizer
+
+
+MaggyZeroAdadelta, MaggyZeroAdagrad, MaggyZeroAdam, MaggyZeroAdamW, MaggyZeroSparseAdam, MaggyZeroAdamax, \
+    MaggyZeroASGD, MaggyZeroLBFGS, MaggyZeroRMSprop, MaggyZeroRprop, MaggyZeroSGD = [
+        make_zero_optimizer(getattr(torch.optim, n)) for n in _ZERO_CLASSES]
+
+
+@contextlib.contextmanager
+def patched_optimizers(zero_lvl: int):
+    """Swap ``torch.optim.<X>`` for the ZeRO variants while the block runs (``zero_lvl`` in 1..2)."""
+    if zero_lvl not in (1, 2):
+        yield
+        return
+    saved = {n: getattr(torch.optim, n) for n in _ZERO_CLASSES}
+    try:
+        for n in _ZERO_CLASSES:
+            setattr(torch.optim, n, make_zero_optimizer(saved[n]))
+        yield
+    finally:
+        for n, cls in saved.items():
+            setattr(torch.optim, n, cls)

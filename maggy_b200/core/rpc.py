@@ -176,7 +176,7 @@ class DriverChannel:
     # -- liveness --------------------------------------------------------------------------------
     def heartbeat_age_s(self, worker: int) -> float:
         hb = int(self.lib.mgr_worker_heartbeat(self.h, worker))
-        return float("inf") if hb == 0 else (now_ns() - hb) / 1e9
+        return 0.0 if hb == 0 else max(0.0, (now_ns() - hb) / 1e9)  # 0: has not started beating yet
 
     def worker_state(self, worker: int) -> int:
         return int(self.lib.mgr_worker_state(self.h, worker))

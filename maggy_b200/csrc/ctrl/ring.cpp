@@ -406,6 +406,7 @@ int mgr_register(void* hv, uint32_t w, uint32_t attempt, uint32_t pid) {
   c->ack_seq = load_acq(&c->assign_seq);
   // a predecessor may have died between writing a blob and the driver consuming it
   store_rel(&c->blob_seq, load_acq(&c->blob_ack));
+  store_rel(&c->heartbeat_ns, now_ns());  // before the state flips: liveness checks key on the state
   store_rel(&c->state, static_cast<uint32_t>(MG_W_REGISTERED));
   return post_record(h, w, MG_REC_REG, 0, 0, 0.0, attempt);
 }

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #define MG_DEVICE __device__ __forceinline__
 
@@ -78,8 +79,25 @@ MG_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// Bounded wait: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
+// try_wait itself sleeps in hardware for up to ~1 us per probe, so the bound is tens of seconds.
+#ifndef MG_MBAR_TIMEOUT_NS
+#define MG_MBAR_TIMEOUT_NS 8000000000ull  // 8 s: far beyond any legitimate wait inside one kernel
+#endif
 MG_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xFFF) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > MG_MBAR_TIMEOUT_NS) {
+        printf("maggy_b200: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n",
+               static_cast<int>(blockIdx.x), static_cast<int>(threadIdx.x), smem_u32(bar), parity);
+        __trap();
+      }
+    }
   }
 }
 

@@ -47,15 +47,22 @@ struct GemmParams {
   int epi;
   int out_f32;     // 0: bf16 output, 1: fp32 output
   int accumulate;  // 1: C += result
+  int tma_store;   // 1: epilogue stages bf16 tiles in smem and writes them with TMA (fast path)
+  int splits;      // split-K factor (>1: fp32 partials go to `ws`, reduced by splitk_reduce_kernel)
+  int kb_per_split;
+  float* ws;       // [splits][M][N] fp32
   int num_m_blocks, num_n_blocks, num_k_blocks;
 };
+
+constexpr int kStageOutBytes = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
 
 template <int BLOCK_N, int STAGES>
 struct SmemLayout {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kOutOffset = STAGES * kStageBytes;  // 1024-aligned (stage sizes are multiples of 16 KB)
+  static constexpr int kBarOffset = kOutOffset + kStageOutBytes;
   static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16;
 };
 
@@ -71,10 +78,22 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int&
   n_blk = r / gsz;
 }
 
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                    pack_bf16x2(v[6], v[7]));
+}
+
 template <int BLOCK_N, int STAGES, int A_MAJOR, int B_MAJOR>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
-                         const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tma_b,
+                         const __grid_constant__ CUtensorMap tma_c,
+                         const __grid_constant__ CUtensorMap tma_aux, const GemmParams p) {
   using L = SmemLayout<BLOCK_N, STAGES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is only guaranteed 16B aligned by the ABI: round up to the 1024B swizzle atom
@@ -89,11 +108,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int num_units = num_tiles * p.splits;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // 256 or 512: power of two
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (p.tma_store) {
+      tma_prefetch_desc(&tma_c);
+      if (p.epi == EPI_BIAS_GELU) tma_prefetch_desc(&tma_aux);
+    }
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -120,11 +144,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int tile = unit % num_tiles, split = unit / num_tiles;
         int m_blk, n_blk;
         tile_coords(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
         const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
@@ -159,11 +186,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int split = unit / num_tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
@@ -179,10 +209,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
             const uint64_t db = (B_MAJOR == 0)
                                     ? make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024)
                                     : make_smem_desc_sw128(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024);
-            umma_f16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[as]);
+          if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -195,122 +225,205 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   } else if (warp_idx >= kEpiWarpBase) {
     // ============================ epilogue ================================
     const int q = warp_idx - kEpiWarpBase;  // == warp_idx % 4: TMEM lane quarter this warp may read
+    uint8_t* out_stage = smem + L::kOutOffset + q * 8192;  // two 4 KB buffers for this warp
+    int obuf = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int tile = unit % num_tiles, split = unit / num_tiles;
       int m_blk, n_blk;
       tile_coords(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
-      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      const int row0 = m_blk * BLOCK_M + q * 32;
+      const int row = row0 + lane;
       const int n0 = n_blk * BLOCK_N;
       const bool row_ok = row < p.M;
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        float v[32];
+
+      if (p.tma_store) {
+        // ---------------- fast path: bf16 tile -> swizzled smem -> TMA store -----------------------
+        const bool has_bias = p.bias != nullptr && (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU ||
+                                                    p.epi == EPI_BIAS_RESIDUAL);
+        const bool reads_aux = p.epi == EPI_DGELU || p.epi == EPI_BIAS_RESIDUAL;
+        const __nv_bfloat16* aux_row = p.aux + static_cast<long long>(row) * p.ld_aux;
+        uint4 aux_cur[8], aux_nxt[8];
+        if (reads_aux && row_ok) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        const bool full_chunk = col0 + 32 <= p.N;
-        if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RESIDUAL) {
-          if (p.bias != nullptr) {
+          for (int j = 0; j < 8; ++j)
+            if (n0 + j * 8 + 8 <= p.N) aux_cur[j] = *reinterpret_cast<const uint4*>(aux_row + n0 + j * 8);
+        }
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        constexpr int kChunks = BLOCK_N / 64;
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c) {
+          const int col0 = n0 + c * 64;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(taddr + c * 64, r0);
+          tmem_ld_32x32b_x32(taddr + c * 64 + 32, r1);
+          // overlap the TMEM read with the bias / next-chunk aux loads
+          uint4 bias_v[8];
+          if (has_bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              bias_v[j] = (col0 + j * 8 + 8 <= p.N)
+                              ? __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + j * 8))
+                              : make_uint4(0, 0, 0, 0);
+          }
+          if (reads_aux && row_ok && c + 1 < kChunks) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (col0 + 64 + j * 8 + 8 <= p.N)
+                aux_nxt[j] = *reinterpret_cast<const uint4*>(aux_row + col0 + 64 + j * 8);
+          }
+          tmem_ld_wait();
+          if (c == kChunks - 1 || col0 + 64 >= p.N) {
+            // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp now
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          }
+          float v[64];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] = __uint_as_float(r0[i]);
+            v[32 + i] = __uint_as_float(r1[i]);
+          }
+          if (has_bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float b[8];
+              unpack8(bias_v[j], b);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) v[j * 8 + t] += b[t];
+            }
+          }
+          auto stage_and_store = [&](const CUtensorMap* map) {
+            if (lane == 0) tma_store_wait_read<1>();  // the buffer we are about to fill is free again
+            __syncwarp();
+            uint8_t* buf = out_stage + obuf * 4096 + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(buf + ((j ^ (lane & 7)) << 4)) = pack8(&v[j * 8]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(map, out_stage + obuf * 4096, col0, row0);
+              tma_store_commit();
+            }
+            obuf ^= 1;
+          };
+          if (p.epi == EPI_BIAS_GELU) {
+            stage_and_store(&tma_aux);  // pre-activation, needed by backward
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = gelu_tanh(v[i]);
+          } else if (reads_aux) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a[8];
+              unpack8(aux_cur[j], a);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                if (p.epi == EPI_DGELU) v[j * 8 + t] *= dgelu_tanh(a[t]);
+                else v[j * 8 + t] += a[t];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) aux_cur[j] = aux_nxt[j];
+          }
+          stage_and_store(&tma_c);
+        }
+      } else {
+        // ---------------- general path: fp32 / accumulate / split-K partials, direct stores ---------
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        float* ws_base = p.splits > 1 ? p.ws + static_cast<long long>(split) * p.M * p.N : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.bias != nullptr &&
+              (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RESIDUAL)) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (col0 + j * 8 + 8 <= p.N) {
-                uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + j * 8));
-                float2 f0 = unpack_bf16x2(b.x), f1 = unpack_bf16x2(b.y), f2 = unpack_bf16x2(b.z),
-                       f3 = unpack_bf16x2(b.w);
-                v[j * 8 + 0] += f0.x; v[j * 8 + 1] += f0.y; v[j * 8 + 2] += f1.x; v[j * 8 + 3] += f1.y;
-                v[j * 8 + 4] += f2.x; v[j * 8 + 5] += f2.y; v[j * 8 + 6] += f3.x; v[j * 8 + 7] += f3.y;
+                float b[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias + col0 + j * 8)), b);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[j * 8 + t] += b[t];
               }
             }
           }
-        }
-        if (row_ok) {
-          if (p.epi == EPI_BIAS_GELU) {
-            __nv_bfloat16* auxp = p.aux + static_cast<long long>(row) * p.ld_aux + col0;
+          if (row_ok) {
+            if (p.epi == EPI_BIAS_GELU) {
+              __nv_bfloat16* auxp = p.aux + static_cast<long long>(row) * p.ld_aux + col0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (col0 + j * 8 + 8 <= p.N) {
-                uint4 o;
-                o.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]);
-                o.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
-                o.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
-                o.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
-                *reinterpret_cast<uint4*>(auxp + j * 8) = o;
-              }
-            }
+              for (int j = 0; j < 4; ++j)
+                if (col0 + j * 8 + 8 <= p.N) *reinterpret_cast<uint4*>(auxp + j * 8) = pack8(&v[j * 8]);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
-          } else if (p.epi == EPI_DGELU || p.epi == EPI_BIAS_RESIDUAL) {
-            const __nv_bfloat16* auxp = p.aux + static_cast<long long>(row) * p.ld_aux + col0;
+              for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+            } else if (p.epi == EPI_DGELU || p.epi == EPI_BIAS_RESIDUAL) {
+              const __nv_bfloat16* auxp = p.aux + static_cast<long long>(row) * p.ld_aux + col0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (col0 + j * 8 + 8 <= p.N) {
-                uint4 a = *reinterpret_cast<const uint4*>(auxp + j * 8);
-                float2 f[4] = {unpack_bf16x2(a.x), unpack_bf16x2(a.y), unpack_bf16x2(a.z),
-                               unpack_bf16x2(a.w)};
+              for (int j = 0; j < 4; ++j) {
+                if (col0 + j * 8 + 8 <= p.N) {
+                  float a[8];
+                  unpack8(*reinterpret_cast<const uint4*>(auxp + j * 8), a);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  if (p.epi == EPI_DGELU) {
-                    v[j * 8 + 2 * t] *= dgelu_tanh(f[t].x);
-                    v[j * 8 + 2 * t + 1] *= dgelu_tanh(f[t].y);
-                  } else {
-                    v[j * 8 + 2 * t] += f[t].x;
-                    v[j * 8 + 2 * t + 1] += f[t].y;
+                  for (int t = 0; t < 8; ++t) {
+                    if (p.epi == EPI_DGELU) v[j * 8 + t] *= dgelu_tanh(a[t]);
+                    else v[j * 8 + t] += a[t];
                   }
                 }
               }
             }
-          }
-          if (p.out_f32) {
-            float* cp = reinterpret_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + col0;
+            if (p.splits > 1 || p.out_f32) {
+              float* cp = p.splits > 1
+                              ? ws_base + static_cast<long long>(row) * p.N + col0
+                              : reinterpret_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + col0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (full_chunk || col0 + j * 4 + 4 <= p.N) {
-                float4 o = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
-                if (p.accumulate) {
-                  float4 old = *reinterpret_cast<float4*>(cp + j * 4);
-                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              for (int j = 0; j < 8; ++j) {
+                if (col0 + j * 4 + 4 <= p.N) {
+                  float4 o = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+                  if (p.accumulate && p.splits == 1) {
+                    float4 old = *reinterpret_cast<float4*>(cp + j * 4);
+                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                  }
+                  *reinterpret_cast<float4*>(cp + j * 4) = o;
                 }
-                *reinterpret_cast<float4*>(cp + j * 4) = o;
               }
-            }
-          } else {
-            __nv_bfloat16* cp =
-                reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + col0;
+            } else {
+              __nv_bfloat16* cp =
+                  reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + col0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (full_chunk || col0 + j * 8 + 8 <= p.N) {
-                if (p.accumulate) {
-                  uint4 old = *reinterpret_cast<const uint4*>(cp + j * 8);
-                  float2 f0 = unpack_bf16x2(old.x), f1 = unpack_bf16x2(old.y),
-                         f2 = unpack_bf16x2(old.z), f3 = unpack_bf16x2(old.w);
-                  v[j * 8 + 0] += f0.x; v[j * 8 + 1] += f0.y; v[j * 8 + 2] += f1.x; v[j * 8 + 3] += f1.y;
-                  v[j * 8 + 4] += f2.x; v[j * 8 + 5] += f2.y; v[j * 8 + 6] += f3.x; v[j * 8 + 7] += f3.y;
+              for (int j = 0; j < 4; ++j) {
+                if (col0 + j * 8 + 8 <= p.N) {
+                  if (p.accumulate) {
+                    float o[8];
+                    unpack8(*reinterpret_cast<const uint4*>(cp + j * 8), o);
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) v[j * 8 + t] += o[t];
+                  }
+                  *reinterpret_cast<uint4*>(cp + j * 8) = pack8(&v[j * 8]);
                 }
-                uint4 o;
-                o.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]);
-                o.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
-                o.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
-                o.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
-                *reinterpret_cast<uint4*>(cp + j * 8) = o;
               }
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
+    if (p.tma_store && lane == 0) tma_store_wait<0>();  // smem must outlive the last bulk store
   }
 
   tc_fence_before();
@@ -318,6 +431,37 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   if (warp_idx == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// out[i] (+)= sum_s ws[s][i]   (split-K second pass; n multiple of 4)
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long n, void* __restrict__ out,
+                     int out_f32, int accumulate) {
+  const long long nvec = n >> 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 acc = reinterpret_cast<const float4*>(ws)[i];
+    for (int s = 1; s < splits; ++s) {
+      float4 t = reinterpret_cast<const float4*>(ws + s * n)[i];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    if (out_f32) {
+      float4* o = reinterpret_cast<float4*>(out) + i;
+      if (accumulate) {
+        float4 t = *o;
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+      *o = acc;
+    } else {
+      uint2* o = reinterpret_cast<uint2*>(out) + i;
+      if (accumulate) {
+        uint2 t = *o;
+        float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y);
+        acc.x += a.x; acc.y += a.y; acc.z += b.x; acc.w += b.y;
+      }
+      *o = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+    }
   }
 }
 
@@ -359,12 +503,16 @@ int make_map_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t ou
 
 int g_num_sms = 0;
 
+struct Maps {
+  CUtensorMap a, b, c, aux;
+};
+
 template <int BLOCK_N, int STAGES, int A_MAJOR, int B_MAJOR>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int max_ctas,
-           cudaStream_t stream) {
+int launch(const Maps& m, const GemmParams& p, int max_ctas, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, STAGES>;
   auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, STAGES, A_MAJOR, B_MAJOR>;
   constexpr int smem_bytes = L::kTotal + 1024;
+  static_assert(smem_bytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
   static bool configured = false;
   if (!configured) {
     cudaError_t e =
@@ -372,46 +520,70 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, in
     if (e != cudaSuccess) return -300 - static_cast<int>(e);
     configured = true;
   }
-  int tiles = p.num_m_blocks * p.num_n_blocks;
-  int grid = tiles < max_ctas ? tiles : max_ctas;
-  kern<<<grid, kNumThreads, smem_bytes, stream>>>(ma, mb, p);
+  int units = p.num_m_blocks * p.num_n_blocks * p.splits;
+  int grid = units < max_ctas ? units : max_ctas;
+  kern<<<grid, kNumThreads, smem_bytes, stream>>>(m.a, m.b, m.c, m.aux, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
 }
 
 template <int BLOCK_N, int STAGES>
-int dispatch_major(int a_major, int b_major, const CUtensorMap& ma, const CUtensorMap& mb,
-                   const GemmParams& p, int max_ctas, cudaStream_t s) {
-  if (a_major == 0 && b_major == 0) return launch<BLOCK_N, STAGES, 0, 0>(ma, mb, p, max_ctas, s);
-  if (a_major == 0 && b_major == 1) return launch<BLOCK_N, STAGES, 0, 1>(ma, mb, p, max_ctas, s);
-  if (a_major == 1 && b_major == 0) return launch<BLOCK_N, STAGES, 1, 0>(ma, mb, p, max_ctas, s);
-  return launch<BLOCK_N, STAGES, 1, 1>(ma, mb, p, max_ctas, s);
+int dispatch_major(int a_major, int b_major, const Maps& m, const GemmParams& p, int max_ctas,
+                   cudaStream_t s) {
+  if (a_major == 0 && b_major == 0) return launch<BLOCK_N, STAGES, 0, 0>(m, p, max_ctas, s);
+  if (a_major == 0 && b_major == 1) return launch<BLOCK_N, STAGES, 0, 1>(m, p, max_ctas, s);
+  if (a_major == 1 && b_major == 0) return launch<BLOCK_N, STAGES, 1, 0>(m, p, max_ctas, s);
+  return launch<BLOCK_N, STAGES, 1, 1>(m, p, max_ctas, s);
+}
+
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_num_sms;
+}
+
+int pick_block_n(int M, int N) {
+  // 128x256 tiles have twice the arithmetic intensity per byte of smem/L2 traffic: use them whenever
+  // N allows; split-K (below) takes care of SM under-utilisation for small outputs
+  return N >= 256 ? 256 : 128;
 }
 
 }  // namespace
+
+// How many K-splits mg_gemm_bf16 will use for (M, N, K) when asked for `splits == 0` (auto): the caller
+// needs it to size the fp32 workspace (splits * M * N floats). 1 means no split-K.
+extern "C" int mg_gemm_auto_splits(int M, int N, int K, int block_n) {
+  if (block_n == 0) block_n = pick_block_n(M, N);
+  long long tiles = static_cast<long long>((M + BLOCK_M - 1) / BLOCK_M) * ((N + block_n - 1) / block_n);
+  int kb = (K + BLOCK_K - 1) / BLOCK_K;
+  int sms = num_sms() > 0 ? num_sms() : 148;
+  if (tiles * 2 > sms || kb < 32) return 1;
+  int s = static_cast<int>(sms / tiles);
+  int max_by_k = kb / 16;  // keep >= 16 k-blocks (1024 of K) per split
+  if (s > max_by_k) s = max_by_k;
+  if (s > 16) s = 16;
+  return s < 1 ? 1 : s;
+}
 
 // C[M,N] = epi( sum_k A(m,k) B(n,k) ).
 //   a_major == 0: A stored [M][K] (row stride lda);  a_major == 1: A stored [K][M] (row stride lda)
 //   b_major == 0: B stored [N][K] (row stride ldb);  b_major == 1: B stored [K][N] (row stride ldb)
 // Alignment: every pointer 16B aligned, lda/ldb/ldc/ld_aux multiples of 8 elements, N % 8 == 0.
 // block_n: 0 = auto, else 128 or 256.  sm_limit: 0 = all SMs, else cap on persistent CTAs.
+// splits: 1 = none, >1 = split-K into `ws` (fp32, splits*M*N floats) + reduce pass (epi must be NONE).
 extern "C" int mg_gemm_bf16(const void* A, const void* B, void* C, const void* bias, void* aux,
                             int M, int N, int K, long long lda, long long ldb, long long ldc,
                             long long ld_aux, int a_major, int b_major, int epi, int out_f32,
-                            int accumulate, int block_n, int sm_limit, void* stream) {
+                            int accumulate, int block_n, int sm_limit, int splits, float* ws,
+                            void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((N % 8) != 0 || (lda % 8) != 0 || (ldb % 8) != 0 || (ldc % (out_f32 ? 4 : 8)) != 0) return -1;
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  if (block_n == 0) {
-    // prefer 128x256 tiles unless that leaves most SMs idle
-    long long t256 = static_cast<long long>((M + 127) / 128) * ((N + 255) / 256);
-    block_n = (N % 256 == 0 || t256 >= 2LL * g_num_sms) && N >= 256 ? 256 : 128;
-    if (t256 < g_num_sms && N >= 128) block_n = 128;
-  }
+  if (block_n == 0) block_n = pick_block_n(M, N);
+  if (splits < 1) splits = 1;
+  if (splits > 1 && (epi != EPI_NONE || ws == nullptr || ldc != N)) return -3;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
   p.C = C; p.ldc = ldc;
@@ -422,18 +594,44 @@ extern "C" int mg_gemm_bf16(const void* A, const void* B, void* C, const void* b
   p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
   p.num_n_blocks = (N + block_n - 1) / block_n;
   p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  if (splits > p.num_k_blocks) splits = p.num_k_blocks;
+  p.kb_per_split = (p.num_k_blocks + splits - 1) / splits;
+  p.splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+  p.ws = ws;
+  p.tma_store = (!out_f32 && !accumulate && p.splits == 1) ? 1 : 0;
 
-  CUtensorMap ma, mb;
+  Maps m;
   int rc;
-  if (a_major == 0) rc = make_map_bf16(&ma, A, K, M, lda, BLOCK_K, BLOCK_M);
-  else              rc = make_map_bf16(&ma, A, M, K, lda, 64, BLOCK_K);
+  if (a_major == 0) rc = make_map_bf16(&m.a, A, K, M, lda, BLOCK_K, BLOCK_M);
+  else              rc = make_map_bf16(&m.a, A, M, K, lda, 64, BLOCK_K);
   if (rc) return rc;
-  if (b_major == 0) rc = make_map_bf16(&mb, B, K, N, ldb, BLOCK_K, block_n);
-  else              rc = make_map_bf16(&mb, B, N, K, ldb, 64, BLOCK_K);
+  if (b_major == 0) rc = make_map_bf16(&m.b, B, K, N, ldb, BLOCK_K, block_n);
+  else              rc = make_map_bf16(&m.b, B, N, K, ldb, 64, BLOCK_K);
   if (rc) return rc - 1000;
+  m.c = m.a;
+  m.aux = m.a;
+  if (p.tma_store) {
+    rc = make_map_bf16(&m.c, C, N, M, ldc, 64, 32);
+    if (rc) return rc - 2000;
+    if (epi == EPI_BIAS_GELU) {
+      rc = make_map_bf16(&m.aux, aux, N, M, ld_aux, 64, 32);
+      if (rc) return rc - 3000;
+    }
+  }
 
-  int max_ctas = (sm_limit > 0 && sm_limit < g_num_sms) ? sm_limit : g_num_sms;
+  int max_ctas = (sm_limit > 0 && sm_limit < num_sms()) ? sm_limit : num_sms();
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return dispatch_major<256, 4>(a_major, b_major, ma, mb, p, max_ctas, s);
-  return dispatch_major<128, 6>(a_major, b_major, ma, mb, p, max_ctas, s);
+  if (block_n == 256) rc = dispatch_major<256, 4>(a_major, b_major, m, p, max_ctas, s);
+  else                rc = dispatch_major<128, 6>(a_major, b_major, m, p, max_ctas, s);
+  if (rc) return rc;
+  if (p.splits > 1) {
+    long long n = static_cast<long long>(M) * N;
+    long long nvec = n >> 2;
+    int grid = static_cast<int>((nvec + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    splitk_reduce_kernel<<<grid, 256, 0, s>>>(ws, p.splits, n, C, out_f32, accumulate);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return -500 - static_cast<int>(e);
+  }
+  return 0;
 }

@@ -19,7 +19,7 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* scrat
 
 // logits [rows, ld] bf16 are overwritten with d(mean loss)/d(logits) * grad_scale.
 // losses[row] = per-row NLL (0 for ignored rows). Columns >= v_real are padding.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 ce_fwd_bwd_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restrict__ targets,
                   float* __restrict__ losses, int v_real, int v_pad, long long ld,
                   float grad_scale, int ignore_index) {
@@ -261,7 +261,10 @@ extern "C" int mg_ce_fwd_bwd(void* logits, const long long* targets, float* loss
     if (e != cudaSuccess) return -300 - static_cast<int>(e);
     configured = smem;
   }
-  ce_fwd_bwd_kernel<<<rows, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  // one row per CTA, the row lives in shared memory: big vocabularies need many threads per CTA to
+  // keep enough 16-byte loads in flight (2 CTAs x 1024 threads per SM at 100 KB/row)
+  const int threads = v_pad >= 16384 ? 1024 : (v_pad >= 4096 ? 512 : 256);
+  ce_fwd_bwd_kernel<<<rows, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<__nv_bfloat16*>(logits), targets, losses, v_real, v_pad, ld, grad_scale,
       ignore_index);
   return check();

@@ -12,7 +12,7 @@ using namespace mg;
 
 constexpr int kMaxVec = 16;  // up to 16 * 32 lanes * 8 = 4096 columns held in registers
 
-template <bool RMS>
+template <bool RMS, int NVEC>
 __global__ void __launch_bounds__(128)
 norm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
                 const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y,
@@ -23,10 +23,10 @@ norm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   if (row >= rows) return;
   const int nvec = C >> 3;  // uint4 vectors per row
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * C);
-  uint4 buf[kMaxVec];
+  uint4 buf[NVEC];
   float s = 0.f, ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < NVEC; ++i) {
     int v = lane + i * 32;
     if (v < nvec) {
       buf[i] = ld_nc_v4(xr + v);
@@ -51,7 +51,7 @@ norm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   const uint4* g4 = reinterpret_cast<const uint4*>(gamma);
   const uint4* b4 = reinterpret_cast<const uint4*>(beta);
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < NVEC; ++i) {
     int v = lane + i * 32;
     if (v < nvec) {
       uint4 g = __ldg(g4 + v);
@@ -158,19 +158,33 @@ norm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __res
   }
 }
 
-__global__ void norm_bwd_finalize_kernel(const float* __restrict__ partial, int nparts, int C,
-                                         __nv_bfloat16* __restrict__ dgamma,
-                                         __nv_bfloat16* __restrict__ dbeta, int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * C) return;
-  int which = c / C, col = c - which * C;
+// one CTA per 32 columns: 8 warps stride over the partial rows, fold through shared memory
+__global__ void __launch_bounds__(256)
+norm_bwd_finalize_kernel(const float* __restrict__ partial, int nparts, int C,
+                         __nv_bfloat16* __restrict__ dgamma, __nv_bfloat16* __restrict__ dbeta,
+                         int accumulate) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;  // column in [0, 2C)
   float acc = 0.f;
-  for (int pidx = 0; pidx < nparts; ++pidx)
-    acc += partial[(static_cast<size_t>(pidx) * 2 + which) * C + col];
-  __nv_bfloat16* dst = which == 0 ? dgamma : dbeta;
-  if (dst == nullptr) return;
-  if (accumulate) acc += __bfloat162float(dst[col]);
-  dst[col] = __float2bfloat16(acc);
+  if (c < 2 * C) {
+    const int which = c / C, col = c - which * C;
+    for (int pidx = warp; pidx < nparts; pidx += 8)
+      acc += partial[(static_cast<size_t>(pidx) * 2 + which) * C + col];
+  }
+  __shared__ float red[8][33];
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c < 2 * C) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    const int which = c / C, col = c - which * C;
+    __nv_bfloat16* dst = which == 0 ? dgamma : dbeta;
+    if (dst != nullptr) {
+      if (accumulate) t += __bfloat162float(dst[col]);
+      dst[col] = __float2bfloat16(t);
+    }
+  }
 }
 
 template <bool RMS>
@@ -200,6 +214,31 @@ int launch_bwd(const void* dy, const void* x, const void* gamma, const float* me
   return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
 }
 
+template <bool RMS, int NVEC>
+void launch_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+                int rows, int C, float eps, cudaStream_t s) {
+  norm_fwd_kernel<RMS, NVEC><<<(rows + 3) / 4, 128, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(gamma),
+      RMS ? nullptr : reinterpret_cast<const __nv_bfloat16*>(beta), reinterpret_cast<__nv_bfloat16*>(y),
+      RMS ? nullptr : mean, rstd, rows, C, eps);
+}
+
+template <bool RMS>
+int dispatch_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+                 int rows, int C, float eps, cudaStream_t s) {
+  // registers hold the row between the statistics pass and the normalise pass: size the buffer to the
+  // row so small hidden sizes keep high occupancy (more bytes in flight per SM)
+  const int nv = ((C >> 3) + 31) / 32;
+  if (nv <= 1) launch_fwd<RMS, 1>(x, gamma, beta, y, mean, rstd, rows, C, eps, s);
+  else if (nv <= 2) launch_fwd<RMS, 2>(x, gamma, beta, y, mean, rstd, rows, C, eps, s);
+  else if (nv <= 3) launch_fwd<RMS, 3>(x, gamma, beta, y, mean, rstd, rows, C, eps, s);
+  else if (nv <= 4) launch_fwd<RMS, 4>(x, gamma, beta, y, mean, rstd, rows, C, eps, s);
+  else if (nv <= 8) launch_fwd<RMS, 8>(x, gamma, beta, y, mean, rstd, rows, C, eps, s);
+  else launch_fwd<RMS, 16>(x, gamma, beta, y, mean, rstd, rows, C, eps, s);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
+}
+
 }  // namespace
 
 // rms: 0 = LayerNorm (mean/rstd saved), 1 = RMSNorm (rstd saved, beta ignored). C % 8 == 0, C <= 4096.
@@ -207,18 +246,8 @@ extern "C" int mg_norm_fwd(const void* x, const void* gamma, const void* beta, v
                            float* rstd, int rows, int C, float eps, int rms, void* stream) {
   if (C % 8 != 0 || C > kMaxVec * 256) return -1;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  int grid = (rows + 3) / 4;
-  if (rms)
-    norm_fwd_kernel<true><<<grid, 128, 0, s>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(gamma),
-        nullptr, reinterpret_cast<__nv_bfloat16*>(y), nullptr, rstd, rows, C, eps);
-  else
-    norm_fwd_kernel<false><<<grid, 128, 0, s>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(gamma),
-        reinterpret_cast<const __nv_bfloat16*>(beta), reinterpret_cast<__nv_bfloat16*>(y), mean,
-        rstd, rows, C, eps);
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
+  return rms ? dispatch_fwd<true>(x, gamma, beta, y, mean, rstd, rows, C, eps, s)
+             : dispatch_fwd<false>(x, gamma, beta, y, mean, rstd, rows, C, eps, s);
 }
 
 // partial: fp32 scratch of at least mg_norm_bwd_grid(rows) * 2 * C floats. C % 8 == 0, C <= 2048.
@@ -236,7 +265,7 @@ extern "C" int mg_norm_bwd(const void* dy, const void* x, const void* gamma, con
   int rc = rms ? launch_bwd<true>(dy, x, gamma, mean, rstd, dx, partial, rows, C, grid, s)
                : launch_bwd<false>(dy, x, gamma, mean, rstd, dx, partial, rows, C, grid, s);
   if (rc) return rc;
-  norm_bwd_finalize_kernel<<<(2 * C + 255) / 256, 256, 0, s>>>(
+  norm_bwd_finalize_kernel<<<(2 * C + 31) / 32, 256, 0, s>>>(
       partial, grid, C, reinterpret_cast<__nv_bfloat16*>(dgamma),
       rms ? nullptr : reinterpret_cast<__nv_bfloat16*>(dbeta), accumulate);
   cudaError_t e = cudaGetLastError();

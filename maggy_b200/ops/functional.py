@@ -65,11 +65,13 @@ def _scratch_f32(key: str, numel: int, device) -> torch.Tensor:
 # thin launchers
 # ------------------------------------------------------------------------------------------------
 def gemm(a, b, *, a_major=K_MAJOR, b_major=K_MAJOR, bias=None, aux=None, epi=EPI_NONE, out=None,
-         out_dtype=torch.bfloat16, accumulate=False, block_n=0, sm_limit=0):
+         out_dtype=torch.bfloat16, accumulate=False, block_n=0, sm_limit=0, splits=None):
     """``C[M,N] = epi(sum_k A(m,k) B(n,k))`` on the tcgen05 kernel.
 
     ``a`` is ``[M,K]`` (``a_major=K_MAJOR``) or ``[K,M]`` (``MN_MAJOR``); ``b`` is ``[N,K]`` or ``[K,N]``.
     Rows may be strided (``stride(0)`` multiple of 8 elements), the inner dimension must be contiguous.
+    ``splits``: split-K factor; ``None`` picks one automatically for small outputs with a long reduction
+    (weight gradients), ``1`` disables it.
     """
     _need_cuda(a, b, bias, aux, out)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16, "bf16 operands"
@@ -87,12 +89,22 @@ def gemm(a, b, *, a_major=K_MAJOR, b_major=K_MAJOR, bias=None, aux=None, epi=EPI
         ld_aux = aux.stride(0)
     if bias is not None:
         assert bias.dtype == torch.bfloat16 and bias.numel() == N and bias.is_contiguous()
-    rc = _lib.cuda().mg_gemm_bf16(
+    lib = _lib.cuda()
+    ws = None
+    if splits is None:
+        splits = 1
+        if epi == EPI_NONE and out.stride(0) == N:
+            splits = lib.mg_gemm_auto_splits(M, N, K, block_n)
+    if splits > 1:
+        assert epi == EPI_NONE and out.stride(0) == N, "split-K needs a plain epilogue and a dense output"
+        ws = _scratch_f32("splitk", splits * M * N, a.device)
+    rc = lib.mg_gemm_bf16(
         a.data_ptr(), b.data_ptr(), out.data_ptr(), _ptr(bias), _ptr(aux), M, N, K,
         a.stride(0), b.stride(0), out.stride(0), ld_aux, a_major, b_major, epi,
-        1 if out.dtype == torch.float32 else 0, 1 if accumulate else 0, block_n, sm_limit, _stream())
+        1 if out.dtype == torch.float32 else 0, 1 if accumulate else 0, block_n, sm_limit, splits,
+        _ptr(ws), _stream())
     _lib.check(rc, f"mg_gemm_bf16(M={M},N={N},K={K})")
-    _count(1)
+    _count(2 if splits > 1 else 1)
     return out
 
 

@@ -81,6 +81,7 @@ class FlatParams:
             p.data = self.params[o:o + k].view(p.shape)
             p.main_grad = self.grads[o:o + k].view(p.shape)
             p._mg_written = False
+            p._maggy_flat = self  # lets the scoped optimizer patch find the arena behind a parameter
             p.grad = None
 
     def _alloc(self, key: str, numel: int, dtype) -> torch.Tensor:

@@ -1,0 +1,224 @@
+"""Control plane on the host-memory rings: protocol state machine, native median-rule policy engine,
+reporter semantics (reference: maggy/core/rpc.py, maggy/core/reporter.py)."""
+import os
+import random
+import threading
+import time
+
+import pytest
+
+from maggy_b200 import Trial
+from maggy_b200.core import exceptions, rpc
+from maggy_b200.core.reporter import Reporter
+from maggy_b200.earlystop import MedianStoppingRule
+
+
+@pytest.fixture
+def chan():
+    d = rpc.DriverChannel(3, ring_slots=64, payload_bytes=1 << 16)
+    yield d
+    d.close()
+
+
+def _drain(d, n, timeout=2.0):
+    out, t0 = [], time.time()
+    while len(out) < n and time.time() - t0 < timeout:
+        out += d.next(0.05)
+    return out
+
+
+def test_register_assign_metric_final_roundtrip(chan):
+    w = rpc.WorkerChannel(chan.name, 1)
+    w.register()
+    (reg,) = _drain(chan, 1)
+    assert reg["type"] == "REG" and reg["partition_id"] == 1 and reg["aux"] == 0
+    assert chan.worker_state(1) == rpc.W_REGISTERED and chan.worker_pid(1) == os.getpid()
+    assert w.wait_assign(0.01) is None                       # nothing assigned yet
+    tid = Trial({"lr": 0.1}).trial_id
+    assert chan.assign(1, tid, {"params": {"lr": 0.1, "fn": lambda x: x * 2}})
+    assert chan.assign(1, tid, {"params": {}}) is False      # slot still occupied
+    got_tid, payload = w.wait_assign(1.0)
+    assert got_tid == tid and payload["params"]["fn"](21) == 42
+    for step, v in enumerate([0.1, 0.2, 0.3]):
+        w.post_metric(tid, v, step)
+    w.post_log(tid, "hello from the worker")
+    msgs = _drain(chan, 4)        # one blob is in flight per worker: the driver acks it by reading it
+    w.post_final(tid, 0.3, {"logs": "bye"})
+    msgs += _drain(chan, 1)
+    assert [m["type"] for m in msgs] == ["METRIC"] * 3 + ["LOG", "FINAL"]
+    assert [m["value"] for m in msgs[:3]] == [0.1, 0.2, 0.3] and [m["step"] for m in msgs[:3]] == [0, 1, 2]
+    assert msgs[3]["data"] == "hello from the worker"
+    assert msgs[4]["data"] == {"metric": 0.3, "logs": "bye"} and msgs[4]["trial_id"] == tid
+    assert all(m["t_ns"] > 0 for m in msgs)
+    w.close()
+
+
+def test_stop_word_and_global_stop(chan):
+    w = rpc.WorkerChannel(chan.name, 0)
+    w.register()
+    tid, other = "00000000000000aa", "00000000000000bb"
+    chan.assign(0, tid, {"params": {}})
+    w.wait_assign(1.0)
+    assert not w.check_stop(tid)
+    chan.stop_trial(0, other)
+    assert not w.check_stop(tid) and w.check_stop(other)
+    chan.stop_trial(0, tid)
+    assert w.check_stop(tid)
+    chan.assign(0, other, {"params": {}})                     # a new assignment clears the stop word
+    w.wait_assign(1.0)
+    assert not w.check_stop(other)
+    t0 = time.time()
+    res = {}
+    th = threading.Thread(target=lambda: res.setdefault("r", w.wait_assign(5.0)))
+    th.start()
+    time.sleep(0.05)
+    chan.gstop()
+    th.join(2)
+    assert res["r"] is rpc.WorkerChannel.GSTOP and time.time() - t0 < 1.0   # futex wake, not a poll period
+    w.close()
+
+
+def test_reregistration_after_death_resets_slot(chan):
+    w = rpc.WorkerChannel(chan.name, 2)
+    w.register()
+    chan.assign(2, "00000000000000cc", {"params": {"a": 1}})
+    w.wait_assign(1.0)
+    w.close()                                                 # "dies" while the trial is assigned
+    w2 = rpc.WorkerChannel(chan.name, 2, attempt=1)
+    w2.register()
+    regs = [m for m in _drain(chan, 2) if m["type"] == "REG"]
+    assert regs[-1]["aux"] == 1                               # driver sees attempt 1 => reschedule (BLACK)
+    assert w2.wait_assign(0.01) is None                       # the consumed assignment is not replayed
+    assert chan.assign(2, "00000000000000cc", {"params": {"a": 1}})
+    assert w2.wait_assign(1.0)[0] == "00000000000000cc"
+    w2.close()
+
+
+def test_ring_wraparound_and_backpressure():
+    d = rpc.DriverChannel(1, ring_slots=8, pump=False)
+    w = rpc.WorkerChannel(d.name, 0)
+    got = []
+    stop = threading.Event()
+
+    def consumer():
+        while not stop.is_set() or len(got) < 200:
+            got.extend(m["step"] for m in d.next(0.001) if m["type"] == "METRIC")
+            if len(got) >= 200:
+                break
+
+    th = threading.Thread(target=consumer)
+    th.start()
+    for i in range(200):                                       # 25 laps around an 8-slot ring
+        w.post_metric("00000000000000dd", float(i), i)
+    stop.set()
+    th.join(5)
+    assert got == list(range(200))
+    w.close()
+    d.close()
+
+
+def test_native_policy_equals_python_median_rule():
+    """Same stream of trials through the native engine and the Python oracle: identical stop decisions."""
+    rng = random.Random(7)
+    for direction in ("max", "min"):
+        d = rpc.DriverChannel(1, ring_slots=256, pump=False)
+        d.configure_policy(True, direction, es_min=2, es_interval=1)
+        w = rpc.WorkerChannel(d.name, 0)
+        finals, native, oracle = [], [], []
+        for n in range(25):
+            t = Trial({"n": n})
+            hist = [rng.random() for _ in range(rng.randint(1, 6))]
+            stopped_native = False
+            for step, v in enumerate(hist):
+                w.post_metric(t.trial_id, v, step)
+                msgs = [m for m in d.next(0) if m["type"] == "METRIC"]
+                t.append_metric({"value": v, "step": step})
+                want = (len(finals) > 2 and
+                        MedianStoppingRule.earlystop_check(t, finals, direction) is not None)
+                if msgs[0]["stopped"]:
+                    stopped_native = True
+                    assert w.check_stop(t.trial_id)
+                if want or stopped_native:
+                    oracle.append((n, step, want))
+                    native.append((n, step, stopped_native))
+                    break
+            w.post_final(t.trial_id, hist[-1])
+            d.next(0)
+            t.final_metric = hist[-1]
+            finals.append(t)
+        assert native == oracle and any(s for _, _, s in native)
+        assert d.policy_stops() == sum(1 for _, _, s in native if s)
+        w.close()
+        d.close()
+
+
+def test_reporter_semantics(tmp_path, chan):
+    w = rpc.WorkerChannel(chan.name, 0)
+    w.register()
+    rep = Reporter(str(tmp_path / "exec.log"), 0, 0, None, w)
+    tid = "00000000000000ee"
+    chan.assign(0, tid, {"params": {}})
+    w.wait_assign(1.0)
+    rep.set_trial_id(tid)
+    rep.init_logger(str(tmp_path / "trial.log"))
+    rep.broadcast(0.5)            # step defaults to previous + 1
+    rep.broadcast(0.6)
+    assert rep.step == 1 and rep.get_data()[0] == 0.6
+    rep.broadcast(0.7, 5)
+    with pytest.raises(exceptions.BroadcastStepValueError):
+        rep.broadcast(0.8, 3)     # steps must not go backwards
+    with pytest.raises(exceptions.BroadcastMetricTypeError):
+        rep.broadcast("0.9")
+    with pytest.raises(exceptions.BroadcastStepTypeError):
+        rep.broadcast(0.9, "7")
+    rep.log("a line for the driver", jupyter=True)
+    msgs = _drain(chan, 3)
+    chan.stop_trial(0, tid)
+    with pytest.raises(exceptions.EarlyStopException) as e:
+        rep.broadcast(0.9, 6)     # the very next broadcast raises
+    assert e.value.metric == 0.9
+    rep.reset()
+    assert rep.step == -1 and rep.metric is None and rep.stop is False
+    msgs += _drain(chan, 3)
+    metrics = [(m["step"], m["value"]) for m in msgs if m["type"] == "METRIC"]
+    assert metrics == [(0, 0.5), (1, 0.6), (5, 0.7), (6, 0.9)]
+    assert any(m["type"] == "LOG" and "a line for the driver" in m["data"] for m in msgs)
+    assert "a line for the driver" in (tmp_path / "trial.log").read_text()
+    rep.close_logger()
+    w.close()
+
+
+def test_reporter_without_channel_and_early_stop_needs_a_metric(tmp_path):
+    rep = Reporter(str(tmp_path / "e.log"), 0, 0, None, None)
+    rep.early_stop()
+    rep.broadcast(1.0)            # no metric had been reported before early_stop(): nothing happens
+    rep.early_stop()
+    with pytest.raises(exceptions.EarlyStopException):
+        rep.broadcast(2.0)
+    rep.close_logger()
+
+
+def test_stop_latency_is_sub_millisecond(chan):
+    """METRIC record -> native policy -> STOP word, measured with the ring's own monotonic stamps."""
+    chan.configure_policy(True, "max", es_min=0, es_interval=1)
+    w = rpc.WorkerChannel(chan.name, 0)
+    good = Trial({"q": 1})
+    for s in range(3):
+        w.post_metric(good.trial_id, 0.9, s)
+    w.post_final(good.trial_id, 0.9)
+    _drain(chan, 4)
+    lat = []
+    for n in range(20):
+        bad = Trial({"bad": n})
+        w.post_metric(bad.trial_id, 0.1, 0)
+        t0 = time.perf_counter()
+        while not w.check_stop(bad.trial_id):
+            assert time.perf_counter() - t0 < 1.0
+        (m,) = [m for m in _drain(chan, 1) if m["type"] == "METRIC"]
+        assert m["stopped"]
+        lat.append((chan.stop_time_ns(0) - m["t_ns"]) / 1e6)
+        w.post_final(bad.trial_id, 0.1)
+        _drain(chan, 1)
+    lat.sort()
+    assert lat[len(lat) // 2] < 5.0, lat   # ms; the reference needs 1-2 heartbeat periods (1-2 s)
+    w.close()

@@ -46,6 +46,45 @@ def test_gemm_mn_major(F, a_major, b_major, M, N, K):
     assert _rel_err(c, ref) < 1e-2
 
 
+@pytest.mark.parametrize("splits", [None, 1, 2, 5])
+@pytest.mark.parametrize("M,N,K,am,bm", [(768, 768, 8192, 1, 1), (3072, 768, 4096, 1, 1), (256, 520, 2048, 0, 0)])
+def test_gemm_split_k(F, splits, M, N, K, am, bm):
+    torch.manual_seed(11)
+    a = torch.randn(M, K, device=DEV, dtype=torch.bfloat16)
+    b = torch.randn(N, K, device=DEV, dtype=torch.bfloat16)
+    a_in = a.t().contiguous() if am else a
+    b_in = b.t().contiguous() if bm else b
+    ref = a.float() @ b.float().t()
+    c = F.gemm(a_in, b_in, a_major=am, b_major=bm, splits=splits)
+    assert _rel_err(c, ref) < 1e-2
+    acc = torch.ones(M, N, device=DEV, dtype=torch.bfloat16)
+    F.gemm(a_in, b_in, a_major=am, b_major=bm, splits=splits, out=acc, accumulate=True)
+    assert _rel_err(acc, ref + 1.0) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 520, 200), (130, 264, 64), (4096, 2304, 768)])
+def test_gemm_epilogues_tails(F, M, N, K):
+    """fused epilogues through the TMA-store path with M / N tails (clipped by the tensor map)."""
+    torch.manual_seed(12)
+    a = torch.randn(M, K, device=DEV, dtype=torch.bfloat16) * 0.5
+    b = torch.randn(N, K, device=DEV, dtype=torch.bfloat16) * 0.1
+    bias = torch.randn(N, device=DEV, dtype=torch.bfloat16)
+    res = torch.randn(M, N, device=DEV, dtype=torch.bfloat16)
+    base = a.float() @ b.float().t()
+    guard = torch.full((M + 8, N + 8), 7.0, device=DEV, dtype=torch.bfloat16)
+    out = guard[:M, :N]
+    F.gemm(a, b, bias=bias, aux=res, epi=F.EPI_BIAS_RESIDUAL, out=out)
+    assert _rel_err(out, base + bias.float() + res.float()) < 1e-2
+    assert (guard[M:, :] == 7.0).all() and (guard[:, N:] == 7.0).all()  # nothing written out of bounds
+    pre = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    act = F.gemm(a, b, bias=bias, aux=pre, epi=F.EPI_BIAS_GELU)
+    assert _rel_err(pre, base + bias.float()) < 1e-2
+    assert _rel_err(act, torch.nn.functional.gelu(base + bias.float(), approximate="tanh")) < 1e-2
+    x = res.float().requires_grad_(True)
+    torch.nn.functional.gelu(x, approximate="tanh").sum().backward()
+    assert _rel_err(F.gemm(a, b, aux=res, epi=F.EPI_DGELU), base * x.grad) < 1.5e-2
+
+
 def test_gemm_epilogues(F):
     torch.manual_seed(2)
     M, N, K = 512, 768, 256

@@ -1,0 +1,287 @@
+"""End-to-end ``experiment.lagom`` runs on CPU worker processes over the shared-memory control plane
+(BASELINE.json config 1: "experiment.lagom random-search 2-param MNIST MLP, CPU (plumbing, no GPU)")."""
+import json
+import os
+import signal
+import time
+
+import pytest
+
+from maggy_b200 import Searchspace, experiment
+from maggy_b200.ablation import AblationStudy
+from maggy_b200.config import (AblationConfig, BaseConfig, HyperparameterOptConfig, OptimizationConfig,
+                               TfDistributedConfig, TorchDistributedConfig)
+from maggy_b200.core.environment.singleton import EnvSing
+from maggy_b200.core.exceptions import NotSupportedError
+
+
+@pytest.fixture(autouse=True)
+def _isolated_logdir(tmp_path, monkeypatch):
+    monkeypatch.setenv("MAGGY_LOG_DIR", str(tmp_path / "experiment_log"))
+    monkeypatch.setenv("MAGGY_NUM_EXECUTORS", "2")
+    EnvSing.reset()
+    yield
+    EnvSing.reset()
+
+
+def _run_dir():
+    env = EnvSing.get_instance()
+    app = sorted(os.listdir(env.log_dir))[-1]
+    run = sorted(os.listdir(os.path.join(env.log_dir, app)), key=int)[-1]
+    return os.path.join(env.log_dir, app, run)
+
+
+def train_quadratic(hparams, reporter):
+    import time
+
+    acc = 0.0
+    for i in range(4):
+        acc = 1.0 - abs(hparams["lr"] - 0.3) - 0.1 / (i + 1)
+        reporter.broadcast(acc, i)
+        time.sleep(0.005)
+    reporter.log("done", jupyter=True)
+    return {"Metric": acc, "extra": hparams["units"]}
+
+
+def test_random_search_end_to_end_and_artefacts():
+    sp = Searchspace(lr=("DOUBLE", [0.0, 1.0]), units=("INTEGER", [8, 64]))
+    cfg = HyperparameterOptConfig(num_trials=8, optimizer="randomsearch", searchspace=sp, direction="max",
+                                  es_policy="none", name="rs", seed=3)
+    res = experiment.lagom(train_quadratic, cfg)
+    assert set(res) >= {"best_id", "best_val", "best_config", "worst_id", "worst_val", "worst_config", "avg",
+                        "metric_list", "num_trials", "early_stopped", "num_epochs", "trial_id"}
+    assert res["num_trials"] == 8 and res["early_stopped"] == 0 and len(res["metric_list"]) == 8
+    assert res["best_val"] == max(res["metric_list"]) and res["worst_val"] == min(res["metric_list"])
+    run = _run_dir()
+    for f in ("maggy.log", "optimizer.log", "result.json", "maggy.json", "executor_0_0.log", "executor_1_0.log"):
+        assert os.path.exists(os.path.join(run, f)), f
+    assert json.load(open(os.path.join(run, "result.json")))["best_id"] == res["best_id"]
+    meta = json.load(open(os.path.join(run, "maggy.json")))
+    assert meta["status"] == "FINISHED" and meta["controller"] == "RandomSearch" and meta["executors"] == 2
+    tdir = os.path.join(run, res["best_id"])
+    for f in ("trial.json", ".hparams.json", ".outputs.json", ".metric", "output.log"):
+        assert os.path.exists(os.path.join(tdir, f)), f
+    trial = json.load(open(os.path.join(tdir, "trial.json")))
+    assert trial["__class__"] == "Trial" and trial["status"] == "FINALIZED" and trial["trial_id"] == res["best_id"]
+    assert trial["step_history"] == [0, 1, 2, 3] and len(trial["metric_history"]) == 4
+    assert trial["final_metric"] == pytest.approx(res["best_val"])
+    assert json.load(open(os.path.join(tdir, ".hparams.json"))) == res["best_config"]
+    outs = json.load(open(os.path.join(tdir, ".outputs.json")))
+    assert outs["Metric"] == pytest.approx(res["best_val"]) and "log" in outs and "extra" in outs
+    assert float(open(os.path.join(tdir, ".metric")).read()) == pytest.approx(res["best_val"])
+    assert "Maggy Optimization 8/8" in open(os.path.join(run, "maggy.log")).read()
+
+
+def train_slow_when_bad(hparams, reporter):
+    import time
+
+    for i in range(200):
+        reporter.broadcast(hparams["q"], i)   # constant quality: bad ones sit below the median forever
+        time.sleep(0.002)
+    return hparams["q"]
+
+
+def test_median_early_stopping_cuts_bad_trials_short():
+    sp = Searchspace(q=("DOUBLE", [0.0, 1.0]))
+    cfg = OptimizationConfig(num_trials=14, optimizer="randomsearch", searchspace=sp, direction="max",
+                             es_policy="median", es_interval=1, es_min=3, name="es", seed=11)
+    t0 = time.time()
+    res = experiment.lagom(train_slow_when_bad, cfg)
+    assert res["num_trials"] == 14 and res["early_stopped"] >= 3
+    run = _run_dir()
+    stopped = []
+    for tid in os.listdir(run):
+        p = os.path.join(run, tid, "trial.json")
+        if os.path.exists(p):
+            t = json.load(open(p))
+            if t["early_stop"]:
+                stopped.append(len(t["metric_history"]))
+    # stopped within a few reports of becoming eligible (trials that started before `es_min` trials had
+    # finished can only be judged late)
+    assert len([n for n in stopped if n < 20]) >= 3, stopped
+    assert time.time() - t0 < 60
+
+
+def test_asha_and_gridsearch_run():
+    sp = Searchspace(lr=("DOUBLE", [0.0, 1.0]), units=("INTEGER", [8, 64]))
+    from maggy_b200.optimizer import Asha
+
+    def train(hparams, reporter):
+        for i in range(int(hparams["budget"])):
+            reporter.broadcast(1.0 - abs(hparams["lr"] - 0.3), i)
+        return 1.0 - abs(hparams["lr"] - 0.3)
+
+    res = experiment.lagom(train, HyperparameterOptConfig(num_trials=16, optimizer=Asha(2, 1, 4), searchspace=sp,
+                                                          direction="max", es_policy="none", name="asha", seed=1))
+    run = _run_dir()
+    budgets = sorted(json.load(open(os.path.join(run, d, "trial.json")))["params"]["budget"]
+                     for d in os.listdir(run) if os.path.exists(os.path.join(run, d, "trial.json")))
+    assert budgets[0] == 1 and budgets[-1] == 4 and res["num_trials"] == len(budgets) <= 16
+    gsp = Searchspace(a=("DISCRETE", [1, 2, 3]), b=("CATEGORICAL", ["x", "y"]))
+    res = experiment.lagom(lambda hparams: float(hparams["a"]) + (0.5 if hparams["b"] == "y" else 0.0),
+                           HyperparameterOptConfig(num_trials=1, optimizer="gridsearch", searchspace=gsp,
+                                                   direction="max", es_policy="none", name="grid"))
+    assert res["num_trials"] == 6 and res["best_val"] == 3.5 and res["best_config"] == {"a": 3, "b": "y"}
+
+
+def test_base_config_runs_in_process():
+    seen = {}
+
+    def train(reporter):
+        reporter.broadcast(0.25)
+        seen["pid"] = os.getpid()
+        return {"accuracy": 0.9, "loss": 0.1}
+
+    res = experiment.lagom(train)  # no config -> BaseConfig
+    assert res == {"test result": {"accuracy": [0.9], "loss": [0.1]}} and seen["pid"] == os.getpid()
+    assert experiment.lagom(lambda: 3, BaseConfig(name="n")) == {"test result": 3.0}
+
+
+def test_ablation_loco_end_to_end():
+    import torch
+
+    def base_model():
+        return torch.nn.Sequential()  # replaced below; LOCO needs named modules
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.stem = torch.nn.Linear(4, 8)
+            self.block_a = torch.nn.Linear(8, 8)
+            self.block_b = torch.nn.Linear(8, 8)
+            self.head = torch.nn.Linear(8, 1)
+
+        def forward(self, x):
+            return self.head(self.block_b(self.block_a(self.stem(x))))
+
+    def dataset(ablated_feature=None):
+        feats = [f for f in ("f0", "f1", "f2", "f3") if f != ablated_feature]
+        return feats
+
+    study = AblationStudy("ds", 1, label_name="y", dataset_generator=dataset)
+    study.features.include("f1", ["f2"])
+    study.model.layers.include("block_a")
+    study.model.layers.include_groups(prefix="block")
+    study.model.set_base_model_generator(Net)
+
+    def train(hparams, reporter):
+        import torch
+
+        model = hparams["model_function"]()
+        feats = hparams["dataset_function"]()
+        n_identity = sum(isinstance(m, torch.nn.Identity) for m in model.modules())
+        return float(len(feats)) + 0.1 * n_identity
+
+    res = experiment.lagom(train, AblationConfig(ablation_study=study, ablator="loco", direction="max", name="abl"))
+    assert res["num_trials"] == 5      # base + 2 features + 1 layer + 1 prefix group
+    assert sorted(round(m, 1) for m in res["metric_list"]) == [3.0, 3.0, 4.0, 4.1, 4.2]
+    assert res["best_config"] == {"ablated_feature": "None", "ablated_layer": "Layers prefixed block"}
+    run = _run_dir()
+    hp = json.load(open(os.path.join(run, res["best_id"], ".hparams.json")))
+    assert hp == {"ablated_feature": "None", "ablated_layer": "Layers prefixed block"}
+
+
+def train_until_killed(hparams, reporter):
+    import os
+    import time
+
+    marker = hparams["marker"]
+    if hparams["victim"] and not os.path.exists(marker):
+        open(marker, "w").write(str(os.getpid()))
+        time.sleep(30)             # the test kills this process while the trial is running
+    for i in range(3):
+        reporter.broadcast(float(hparams["v"]), i)
+    return float(hparams["v"])
+
+
+def test_worker_death_reschedules_the_trial(tmp_path):
+    marker = str(tmp_path / "victim.pid")
+    sp = Searchspace(v=("DISCRETE", [1, 2, 3, 4]), victim=("DISCRETE", [True]), marker=("CATEGORICAL", [marker]))
+    cfg = HyperparameterOptConfig(num_trials=1, optimizer="gridsearch", searchspace=sp, direction="max",
+                                  es_policy="none", name="kill")
+    import threading
+
+    def killer():
+        t0 = time.time()
+        while not os.path.exists(marker) and time.time() - t0 < 60:
+            time.sleep(0.05)
+        time.sleep(0.2)
+        os.kill(int(open(marker).read()), signal.SIGKILL)
+
+    th = threading.Thread(target=killer)
+    th.start()
+    res = experiment.lagom(train_until_killed, cfg)
+    th.join()
+    assert res["num_trials"] == 4 and sorted(res["metric_list"]) == [1.0, 2.0, 3.0, 4.0]
+    log = open(os.path.join(_run_dir(), "maggy.log")).read()
+    assert "died unexpectedly" in log and "rescheduling lost trial" in log
+
+
+def test_train_fn_exception_fails_the_experiment():
+    sp = Searchspace(x=("DOUBLE", [0.0, 1.0]))
+
+    def train(hparams):
+        raise ValueError("boom in user code")
+
+    with pytest.raises(RuntimeError, match="boom in user code"):
+        experiment.lagom(train, HyperparameterOptConfig(num_trials=2, optimizer="randomsearch", searchspace=sp,
+                                                        es_policy="none", name="err"))
+
+
+def test_config_validation():
+    sp = Searchspace(x=("DOUBLE", [0.0, 1.0]))
+    with pytest.raises(ValueError):
+        HyperparameterOptConfig(num_trials=0, optimizer="randomsearch", searchspace=sp)
+    with pytest.raises(ValueError):
+        HyperparameterOptConfig(num_trials=2, optimizer="randomsearch", searchspace=sp, direction="up")
+    with pytest.raises(Exception, match="Unknown Optimizer"):
+        experiment.lagom(lambda: 1, HyperparameterOptConfig(num_trials=2, optimizer="sgd", searchspace=sp))
+    with pytest.raises(ValueError):
+        TorchDistributedConfig(module=None, backend="horovod")
+    with pytest.raises(ValueError):
+        TorchDistributedConfig(module=None, backend="deepspeed")
+    with pytest.raises(NotSupportedError):
+        experiment.lagom(lambda: 1, TfDistributedConfig())
+    with pytest.raises(TypeError):
+        experiment.lagom(lambda: 1, object())
+
+
+def train_dist(module, hparams, reporter):
+    import torch
+    import torch.distributed as dist
+
+    torch.manual_seed(0)
+    model = module(hparams["width"])
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    x = torch.full((4, hparams["width"]), float(rank + 1))
+    for step in range(3):
+        opt.zero_grad()
+        loss = model(x).pow(2).mean()
+        loss.backward()
+        opt.step()
+        reporter.broadcast(loss.item(), step)
+    w = torch.cat([p.detach().flatten() for p in model.parameters()])
+    gathered = [torch.zeros_like(w) for _ in range(world)]
+    dist.all_gather(gathered, w)
+    assert all(torch.allclose(g, gathered[0]) for g in gathered)   # DDP kept the replicas in sync
+    return float(rank)
+
+
+def test_torch_distributed_training_over_gloo():
+    import torch
+
+    class Tiny(torch.nn.Module):
+        def __init__(self, width):
+            super().__init__()
+            self.l = torch.nn.Linear(width, 1)
+
+        def forward(self, x):
+            return self.l(x)
+
+    cfg = TorchDistributedConfig(module=Tiny, hparams={"width": 8}, backend="torch", zero_lvl=1, name="td")
+    res = experiment.lagom(train_dist, cfg)
+    assert res == {"test result": 0.5}     # mean of the ranks' metrics (0 and 1)
+    run = _run_dir()
+    assert os.path.exists(os.path.join(run, "training_logs_0", "output.log"))
+    assert os.path.exists(os.path.join(run, "training_logs_1", ".outputs.json"))
