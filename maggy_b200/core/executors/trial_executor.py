@@ -25,13 +25,15 @@ from ..reporter import Reporter
 _STOP = "__maggy_stop__"
 
 
-def _start_heartbeat(channel, interval_s: float):
+def _start_heartbeat(channel, interval_s: float, reporter=None):
     stop = threading.Event()
 
     def beat():
         while not stop.wait(interval_s):
             try:
                 channel.heartbeat()
+                if reporter is not None and reporter.deferred:
+                    reporter.ship()
             except Exception:
                 return
 
@@ -121,7 +123,10 @@ def trial_executor_loop(spec, channel, worker_id, attempt, gang=None):
         reporter.log(" ".join(str(x) for x in args), True)
 
     builtins.print = maggy_print
-    hb_stop = _start_heartbeat(channel, max(0.2, float(spec.get("hb_interval", 1))))
+    proxy_rpc = os.environ.get("MAGGY_B200_PROXY_REFERENCE_RPC") == "1"
+    reporter.deferred = proxy_rpc
+    hb_stop = _start_heartbeat(channel, float(spec.get("hb_interval", 1)) if proxy_rpc
+                               else max(0.2, float(spec.get("hb_interval", 1))), reporter)
     clean_exit = False
     try:
         channel.register()
@@ -152,6 +157,8 @@ def trial_executor_loop(spec, channel, worker_id, attempt, gang=None):
             _, _, logs = reporter.get_data()
             channel.post_final(trial_id, metric, {"logs": logs, "wall_s": time.time() - t0})
             reporter.reset()
+            if proxy_rpc:
+                time.sleep(1.0)  # reference: the first GET after FINAL races the driver and sleeps 1 s (rpc.py:745-747)
     finally:
         hb_stop.set()
         builtins.print = original_print

@@ -40,6 +40,10 @@ class Reporter:
         self.print_executor = print_executor or (lambda *a, **k: None)
         self.channel = channel
         self._last_log_flush = 0.0
+        # proxy of the reference's mechanism (benchmarks only): metrics are not sent by broadcast() but by a
+        # heartbeat thread calling ship() once per hb_interval, and STOP arrives with that heartbeat
+        self.deferred = False
+        self._shipped_step = None
         env = EnvSing.get_instance()
         if log_file:
             if not env.exists(log_file):
@@ -89,7 +93,7 @@ class Reporter:
                 raise exceptions.BroadcastStepValueError(metric, step, self.step)
             self.step = step
             self.metric = metric
-            if self.channel is not None and self.trial_id is not None:
+            if self.channel is not None and self.trial_id is not None and not self.deferred:
                 if on_device:
                     self.channel.post_metric_device(self.trial_id, metric.detach().reshape(()), int(step))
                 else:
@@ -99,6 +103,17 @@ class Reporter:
                 self._maybe_flush_logs()
             if self.stop:
                 raise exceptions.EarlyStopException(self._metric_value())
+
+    def ship(self):
+        """Reference-style heartbeat: send the latest metric (if new) and pick up a pending STOP."""
+        with self.lock:
+            if self.channel is None or self.trial_id is None or self.metric is None:
+                return
+            if self._shipped_step != self.step:
+                self.channel.post_metric(self.trial_id, float(self._metric_value()), int(self.step))
+                self._shipped_step = self.step
+            if self.channel.check_stop(self.trial_id):
+                self.early_stop()
 
     def _metric_value(self):
         m = self.metric
@@ -154,6 +169,7 @@ class Reporter:
             self.step = -1
             self.stop = False
             self.trial_id = None
+            self._shipped_step = None
             if self.fd:
                 self.fd.flush()
             if self.trial_fd:

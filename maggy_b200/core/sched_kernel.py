@@ -1,0 +1,81 @@
+"""Host handle of the persistent device scheduler (K9, csrc/ctrl/ring_device.cu ``sched_kernel``).
+
+``DeviceScheduler(channel, ...).start()`` maps the control segment into the CUDA address space and launches
+a single-CTA kernel on a low-priority stream that keeps polling every worker's rings, evaluates the median
+stopping rule on the device and writes STOP words itself. ``stop()`` raises the quit flag, joins the stream
+and returns the kernel's counters. The Python driver keeps consuming the same records for bookkeeping.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from ..ops import _lib
+from . import rpc
+
+
+class DeviceScheduler:
+    def __init__(self, channel: "rpc.DriverChannel", direction: str = "max", es_min: int = 10, es_interval: int = 1,
+                 max_steps: int = 1024, cap_final: int = 1024, device="cuda:0"):
+        self.ch = channel
+        self.device = torch.device(device)
+        self.direction = 1 if direction == "max" else -1
+        self.es_min, self.es_interval = es_min, es_interval
+        self.max_steps, self.cap_final = max_steps, cap_final
+        self.cu = _lib.cuda()
+        u64, P, u32, i32 = ctypes.c_ulonglong, ctypes.c_void_p, ctypes.c_uint, ctypes.c_int
+        self._u64 = u64
+        self.cu.mg_ring_map.argtypes, self.cu.mg_ring_map.restype = [P, u64], u64
+        self.cu.mg_sched_scratch_bytes.argtypes, self.cu.mg_sched_scratch_bytes.restype = [u32, u32, u32], u64
+        self.cu.mg_sched_start.argtypes = [u64, u64, u64, u64, u64, u32, u32, i32, u32, u32, u32, u32, P, u64, P]
+        self.cu.mg_sched_start.restype = i32
+        self.stream = None
+        self.running = False
+
+    def start(self):
+        host = self.ch.lib
+        h = self.ch.h
+        with torch.cuda.device(self.device):
+            base = self.cu.mg_ring_map(host.mgr_base(h), host.mgr_bytes(h))
+            if not base:
+                raise RuntimeError("could not map the control segment into the CUDA address space")
+            W = self.ch.num_workers
+            nbytes = int(self.cu.mg_sched_scratch_bytes(W, self.max_steps, self.cap_final))
+            self.scratch = torch.zeros(nbytes + 64, dtype=torch.uint8, device=self.device)
+            # quit flag lives in pinned host memory the kernel polls through its device mapping
+            self.quit = torch.zeros(16, dtype=torch.int32).pin_memory()
+            quit_dev = self.cu.mg_ring_map(self.quit.data_ptr(), self.quit.numel() * 4)
+            if not quit_dev:
+                quit_dev = self.quit.data_ptr()  # pinned memory is UVA-addressable from the device
+            lo, _hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, 0)
+            self.stream = torch.cuda.Stream(device=self.device, priority=0)
+            u64 = self._u64
+            host.mgr_off_host_ring.argtypes, host.mgr_off_host_ring.restype = [ctypes.c_void_p, ctypes.c_uint32], u64
+            host.mgr_ring_stride.argtypes, host.mgr_ring_stride.restype = [ctypes.c_void_p], u64
+            off_ctl = int(host.mgr_off_ctl(h, 0))
+            off_dev0 = int(host.mgr_off_dev_ring(h, 0))
+            off_host0 = int(host.mgr_off_host_ring(h, 0))
+            ring_stride = int(host.mgr_ring_stride(h))
+            rc = self.cu.mg_sched_start(base, off_ctl, off_host0, off_dev0, ring_stride, W,
+                                        int(host.mgr_ring_slots(h)), self.direction, self.es_min, self.es_interval,
+                                        self.max_steps, self.cap_final, self.scratch.data_ptr(), quit_dev,
+                                        self.stream.cuda_stream)
+            if rc != 0:
+                raise RuntimeError(f"mg_sched_start failed: {rc}")
+        self.running = True
+        return self
+
+    def stats(self) -> dict:
+        W = self.ch.num_workers
+        off = 4 * self.cap_final * self.max_steps + 4 * self.cap_final + 8 + 4 * W * self.max_steps
+        off = (off + 7) // 8 * 8 + 8 * W * 2
+        raw = self.scratch[off:off + 32].cpu().view(torch.int64).tolist()
+        return {"polls": raw[0], "metrics": raw[1], "stops": raw[2], "finals": raw[3]}
+
+    def stop(self) -> dict:
+        if self.running:
+            self.quit[0] = 1
+            self.stream.synchronize()
+            self.running = False
+        return self.stats()

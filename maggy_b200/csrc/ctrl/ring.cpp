@@ -362,6 +362,11 @@ uint64_t mgr_off_dev_ring(void* hv, uint32_t w) {
   Handle* h = static_cast<Handle*>(hv);
   return h->hdr()->off_dev_ring + static_cast<uint64_t>(w) * h->hdr()->ring_stride;
 }
+uint64_t mgr_off_host_ring(void* hv, uint32_t w) {
+  Handle* h = static_cast<Handle*>(hv);
+  return h->hdr()->off_host_ring + static_cast<uint64_t>(w) * h->hdr()->ring_stride;
+}
+uint64_t mgr_ring_stride(void* hv) { return static_cast<Handle*>(hv)->hdr()->ring_stride; }
 uint64_t mgr_off_ctl(void* hv, uint32_t w) {
   Handle* h = static_cast<Handle*>(hv);
   return h->hdr()->off_ctl + static_cast<uint64_t>(w) * sizeof(MgWorkerCtl);

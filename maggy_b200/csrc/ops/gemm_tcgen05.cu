@@ -109,7 +109,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int num_units = num_tiles * p.splits;
-  constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // 256 or 512: power of two
+  constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 256) ? 256 : 512;  // allocation must be a power of two
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -546,9 +546,20 @@ int num_sms() {
 }
 
 int pick_block_n(int M, int N) {
-  // 128x256 tiles have twice the arithmetic intensity per byte of smem/L2 traffic: use them whenever
-  // N allows; split-K (below) takes care of SM under-utilisation for small outputs
-  return N >= 256 ? 256 : 128;
+  // Wide tiles have the best arithmetic intensity per byte of smem/L2 traffic, so 128-wide tiles are only
+  // for narrow outputs. Between 256 and 192 pick the one that wastes less of the last wave of the
+  // persistent grid (e.g. M=32768, N=768: 768 tiles of 256 = 5.2 waves -> 6; 1024 tiles of 192 = 6.9 -> 7,
+  // i.e. 1344 vs 1536 column-units of work).
+  if (N < 192) return 128;
+  const int sms = num_sms() > 0 ? num_sms() : 148;
+  const long long mb = (M + BLOCK_M - 1) / BLOCK_M;
+  auto cost = [&](int bn) {
+    long long tiles = mb * ((N + bn - 1) / bn);
+    long long waves = (tiles + sms - 1) / sms;
+    return waves * bn;
+  };
+  if (N < 256) return 192;
+  return cost(192) < cost(256) ? 192 : 256;
 }
 
 }  // namespace
@@ -572,7 +583,7 @@ extern "C" int mg_gemm_auto_splits(int M, int N, int K, int block_n) {
 //   a_major == 0: A stored [M][K] (row stride lda);  a_major == 1: A stored [K][M] (row stride lda)
 //   b_major == 0: B stored [N][K] (row stride ldb);  b_major == 1: B stored [K][N] (row stride ldb)
 // Alignment: every pointer 16B aligned, lda/ldb/ldc/ld_aux multiples of 8 elements, N % 8 == 0.
-// block_n: 0 = auto, else 128 or 256.  sm_limit: 0 = all SMs, else cap on persistent CTAs.
+// block_n: 0 = auto, else 128, 192 or 256.  sm_limit: 0 = all SMs, else cap on persistent CTAs.
 // splits: 1 = none, >1 = split-K into `ws` (fp32, splits*M*N floats) + reduce pass (epi must be NONE).
 extern "C" int mg_gemm_bf16(const void* A, const void* B, void* C, const void* bias, void* aux,
                             int M, int N, int K, long long lda, long long ldb, long long ldc,
@@ -621,8 +632,10 @@ extern "C" int mg_gemm_bf16(const void* A, const void* B, void* C, const void* b
 
   int max_ctas = (sm_limit > 0 && sm_limit < num_sms()) ? sm_limit : num_sms();
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) rc = dispatch_major<256, 4>(a_major, b_major, m, p, max_ctas, s);
-  else                rc = dispatch_major<128, 6>(a_major, b_major, m, p, max_ctas, s);
+  if (block_n == 256)      rc = dispatch_major<256, 4>(a_major, b_major, m, p, max_ctas, s);
+  else if (block_n == 192) rc = dispatch_major<192, 4>(a_major, b_major, m, p, max_ctas, s);
+  else if (block_n == 128) rc = dispatch_major<128, 6>(a_major, b_major, m, p, max_ctas, s);
+  else return -4;
   if (rc) return rc;
   if (p.splits > 1) {
     long long n = static_cast<long long>(M) * N;

@@ -180,6 +180,10 @@ embed_fwd_kernel(const long long* __restrict__ idx, const __nv_bfloat16* __restr
   const uint4* pe = reinterpret_cast<const uint4*>(wpe + static_cast<size_t>(tok % T) * C);
   uint4* o = reinterpret_cast<uint4*>(out + static_cast<size_t>(tok) * C);
   for (int v = lane; v < (C >> 3); v += 32) {
+    if (wpe == nullptr) {  // token embedding only (rotary-position models)
+      o[v] = __ldg(te + v);
+      continue;
+    }
     uint4 a = __ldg(te + v), b = __ldg(pe + v);
     const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
     uint32_t r[4];
@@ -321,8 +325,9 @@ extern "C" int mg_embed_bwd(const long long* idx, const void* dout, void* dwte, 
   embed_bwd_wte_kernel<<<(B * T + 3) / 4, 128, 0, s>>>(
       idx, reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<__nv_bfloat16*>(dwte),
       B * T, C);
-  embed_bwd_wpe_kernel<<<(T + 3) / 4, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dout),
-                                                   reinterpret_cast<__nv_bfloat16*>(dwpe), B, T, C,
-                                                   accumulate_wpe);
+  if (dwpe != nullptr)
+    embed_bwd_wpe_kernel<<<(T + 3) / 4, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dout),
+                                                     reinterpret_cast<__nv_bfloat16*>(dwpe), B, T, C,
+                                                     accumulate_wpe);
   return check();
 }

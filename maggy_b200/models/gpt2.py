@@ -81,6 +81,8 @@ class Block(nn.Module):
 
 
 class GPT2(nn.Module):
+    maggy_b200_native = True
+
     def __init__(self, cfg: GPT2Config):
         super().__init__()
         self.cfg = cfg

@@ -376,12 +376,14 @@ def cross_entropy(logits, targets, v_real=None, ignore_index=-100, unit_grad=Tru
 
 
 class _Embedding(torch.autograd.Function):
+    """out[b, t] = wte[idx[b, t]] (+ wpe[t]); ``wpe`` may be None (rotary-position models)."""
+
     @staticmethod
     def forward(ctx, idx, wte, wpe):
         B, T = idx.shape
         C = wte.shape[1]
         out = torch.empty((B, T, C), dtype=torch.bfloat16, device=wte.device)
-        rc = _lib.cuda().mg_embed_fwd(idx.data_ptr(), wte.data_ptr(), wpe.data_ptr(), out.data_ptr(),
+        rc = _lib.cuda().mg_embed_fwd(idx.data_ptr(), wte.data_ptr(), _ptr(wpe), out.data_ptr(),
                                       B * T, T, C, _stream())
         _lib.check(rc, "mg_embed_fwd")
         _count(1)
@@ -397,26 +399,30 @@ class _Embedding(torch.autograd.Function):
         C = wte.shape[1]
         dout = dout.contiguous()
         use_main = getattr(wte, "main_grad", None) is not None
+        dwpe, acc_wpe = None, False
         if use_main:
-            dwte, dwpe = wte.main_grad, wpe.main_grad
+            dwte = wte.main_grad
             if not getattr(wte, "_mg_written", False):
                 dwte.zero_()
-            acc_wpe = bool(getattr(wpe, "_mg_written", False))
-            if not acc_wpe and T < wpe.shape[0]:
-                dwpe[T:].zero_()
-            wte._mg_written = wpe._mg_written = True
+            wte._mg_written = True
+            if wpe is not None:
+                dwpe = wpe.main_grad
+                acc_wpe = bool(getattr(wpe, "_mg_written", False))
+                if not acc_wpe and T < wpe.shape[0]:
+                    dwpe[T:].zero_()
+                wpe._mg_written = True
         else:
             dwte = torch.zeros_like(wte)
-            dwpe = torch.zeros_like(wpe) if T < wpe.shape[0] else torch.empty_like(wpe)
-            acc_wpe = False
-        rc = _lib.cuda().mg_embed_bwd(idx.data_ptr(), dout.data_ptr(), dwte.data_ptr(), dwpe.data_ptr(),
+            if wpe is not None:
+                dwpe = torch.zeros_like(wpe) if T < wpe.shape[0] else torch.empty_like(wpe)
+        rc = _lib.cuda().mg_embed_bwd(idx.data_ptr(), dout.data_ptr(), dwte.data_ptr(), _ptr(dwpe),
                                       B, T, C, 1 if acc_wpe else 0, _stream())
         _lib.check(rc, "mg_embed_bwd")
-        _count(2)
+        _count(2 if dwpe is not None else 1)
         if use_main:
             return None, None, None
         return None, dwte, dwpe
 
 
-def embedding(idx, wte, wpe):
+def embedding(idx, wte, wpe=None):
     return _Embedding.apply(idx, wte, wpe)

@@ -58,7 +58,7 @@ def main():
         ta = a if am == 0 else a.t()
         tb = b.t() if bm == 0 else b
         res = {}
-        for bn in (128, 256):
+        for bn in (0, 192, 256):
             try:
                 res[bn] = timeit(lambda: F.gemm(a, b, a_major=am, b_major=bm, out=out, block_n=bn), flush)
             except Exception as e:  # noqa: BLE001
@@ -67,11 +67,11 @@ def main():
         t_ref = timeit(lambda: torch.matmul(ta, tb, out=out), flush)
         fl = 2.0 * m * n * k
         row = {"shape": name, "M": m, "N": n, "K": k,
-               "ours_bn128_ms": res[128], "ours_bn256_ms": res[256], "cublas_ms": t_ref,
-               "ours_tflops": fl / (min(res[128], res[256]) * 1e-3) / 1e12, "cublas_tflops": fl / (t_ref * 1e-3) / 1e12}
+               "ours_auto_ms": res[0], "ours_bn192_ms": res[192], "ours_bn256_ms": res[256], "cublas_ms": t_ref,
+               "ours_tflops": fl / (res[0] * 1e-3) / 1e12, "cublas_tflops": fl / (t_ref * 1e-3) / 1e12}
         rows.append(row)
-        print(f"{name:42s} ours bn128 {res[128]:8.3f} ms  bn256 {res[256]:8.3f} ms ({row['ours_tflops']:7.1f} TF)"
-              f"   cuBLAS {t_ref:8.3f} ms ({row['cublas_tflops']:7.1f} TF)", flush=True)
+        print(f"{name:42s} ours auto {res[0]:8.3f} ms ({row['ours_tflops']:7.1f} TF) bn192 {res[192]:8.3f} bn256 {res[256]:8.3f}"
+              f"   cuBLAS {t_ref:8.3f} ms ({row['cublas_tflops']:7.1f} TF)  ratio {t_ref / res[0]:.2f}", flush=True)
     if args.out:
         json.dump(rows, open(args.out, "w"), indent=1)
 

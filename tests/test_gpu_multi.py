@@ -1,0 +1,19 @@
+"""Multi-GPU checks (need >= 2 devices; skipped otherwise): fused reduce-scatter+Adam+all-gather kernel."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_fused_rs_adam_matches_nccl_oracle():
+    import torch
+
+    n = min(torch.cuda.device_count(), 8)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "multi", "rs_adam_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0 and "RS_ADAM_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
