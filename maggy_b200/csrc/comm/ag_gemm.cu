@@ -1,0 +1,412 @@
+// K3 — parameter all-gather fused into the consuming tcgen05 GEMM (sm_100a, NVLink 5 / NVSwitch).
+//
+//   y[M, N] = x[M, K] · Wᵀ (+ bias),   W = [N, K] sharded by rows over `world` ranks (ZeRO-3 / FSDP layout)
+//
+// The reference reaches this through fairscale FSDP: an NCCL all-gather of the flat parameter, THEN the
+// cuBLAS GEMM (maggy/core/patching/modules.py:75-95). Here one persistent kernel does both:
+//   * `n_copy` CTAs are *gather* CTAs: they pull the remote weight shards straight out of the owners' HBM
+//     over NVLink (16-byte peer loads, 8 in flight per thread) into a local gathered buffer, one 256-row
+//     block at a time, nearest shard first, and publish `ready[n_blk]` with a release store;
+//   * the other CTAs are the usual TMA-producer / tcgen05-MMA / epilogue pipeline. Output tiles are
+//     visited local-shard-first, so the tensor cores start immediately on weights that are already here
+//     and by the time they need a remote block its copy has landed (the producer warp acquires
+//     `ready[n_blk]` before issuing that tile's TMA loads);
+//   * cross-GPU ordering uses symmetric flag words: "my shard is ready for epoch e" before any peer reads
+//     it and "I am done reading" before the kernel retires, so plain stream order protects the owner's next
+//     optimizer step. No NCCL call, no separate collective launch.
+#include "../include/mg_ptx.cuh"
+
+#include <mutex>
+
+namespace {
+using namespace mg;
+
+constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, UMMA_K = 16, STAGES = 4;
+constexpr int kNumThreads = 256, kEpiWarpBase = 4, kMaxWorld = 8;
+constexpr int kABytes = BLOCK_M * BLOCK_K * 2, kBBytes = BLOCK_N * BLOCK_K * 2;
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kOutOffset = STAGES * kStageBytes;
+constexpr int kBarOffset = kOutOffset + 4 * 2 * 4096;
+constexpr int kSmemTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16;
+
+struct AgParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  const __nv_bfloat16* bias;
+  // gather
+  const __nv_bfloat16* shard_peer[kMaxWorld];  // every rank's weight shard [N/world, K] (peer-mapped)
+  __nv_bfloat16* gathered;                     // local [N, K] staging buffer (remote rows only are written)
+  uint32_t* ready;                             // [num_n_blocks], zeroed before launch
+  uint32_t* flag_peer[kMaxWorld];              // symmetric words: [0..8) shard-ready epochs, [8..16) done-reading
+  uint32_t* local_sync;                        // [0] finished-CTA counter, [1] launches completed (epoch source)
+  int rank, world, n_copy;
+  int blocks_per_shard;                        // (N / world) / BLOCK_N
+  uint32_t epoch;                              // 0 = take local_sync[1] + 1 on device
+};
+
+MG_DEVICE uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+MG_DEVICE void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <class Pred>
+MG_DEVICE void spin_until(Pred ready, const char* what) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!ready()) {
+    if ((++spins & 0x3FF) == 0) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000ull) {
+        printf("maggy_b200 ag_gemm: timed out waiting for %s (block %d)\n", what, static_cast<int>(blockIdx.x));
+        __trap();
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+ag_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b_local,
+               const __grid_constant__ CUtensorMap tma_b_gathered, const __grid_constant__ CUtensorMap tma_c,
+               const AgParams p_in) {
+  AgParams p = p_in;
+  if (p.epoch == 0) p.epoch = *reinterpret_cast<volatile uint32_t*>(p.local_sync + 1) + 1;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int first_local_blk = p.rank * p.blocks_per_shard;
+
+  if (static_cast<int>(blockIdx.x) < p.n_copy) {
+    // =========================== gather CTAs ===========================================
+    if (blockIdx.x == 0 && threadIdx.x < p.world) {
+      // tell every peer that my shard may be read for this epoch (my stream already ran my optimizer step)
+      __threadfence_system();
+      st_release_sys_u32(p.flag_peer[threadIdx.x] + p.rank, p.epoch);
+    }
+    const int remote_blocks = p.num_n_blocks - p.blocks_per_shard;
+    const long long blk_elems = static_cast<long long>(BLOCK_N) * p.K;
+    for (int i = blockIdx.x; i < remote_blocks; i += p.n_copy) {
+      // i-th remote block in "nearest shard first" order
+      int n_blk = first_local_blk + p.blocks_per_shard + i;
+      if (n_blk >= p.num_n_blocks) n_blk -= p.num_n_blocks;
+      const int src = n_blk / p.blocks_per_shard;
+      if (threadIdx.x == 0)
+        spin_until([&] { return ld_acquire_sys_u32(p.flag_peer[p.rank] + src) >= p.epoch; }, "peer shard");
+      __syncthreads();
+      const uint4* sp = reinterpret_cast<const uint4*>(
+          p.shard_peer[src] + static_cast<long long>(n_blk - src * p.blocks_per_shard) * blk_elems);
+      uint4* dp = reinterpret_cast<uint4*>(p.gathered + static_cast<long long>(n_blk) * blk_elems);
+      const long long nvec = blk_elems >> 3;
+      long long v = threadIdx.x;
+      for (; v + 7 * kNumThreads < nvec; v += 8 * kNumThreads) {
+        uint4 r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = ld_relaxed_sys_v4(sp + v + j * kNumThreads);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dp[v + j * kNumThreads] = r[j];
+      }
+      for (; v < nvec; v += kNumThreads) dp[v] = ld_relaxed_sys_v4(sp + v);
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) st_release_gpu(p.ready + n_blk, 1u);
+    }
+    // done reading peers: tell them, then (last gather CTA only) wait until everybody is done with MY shard
+    __syncthreads();
+    __shared__ uint32_t is_last;
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      is_last = (atomicAdd(p.local_sync, 1u) == static_cast<uint32_t>(p.n_copy) - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (is_last) {
+      if (threadIdx.x == 0) {
+        p.local_sync[0] = 0;
+        p.local_sync[1] = p.epoch;
+      }
+      if (threadIdx.x < p.world) {
+        const int peer = threadIdx.x;
+        st_release_sys_u32(p.flag_peer[peer] + kMaxWorld + p.rank, p.epoch);
+        spin_until([&] { return ld_acquire_sys_u32(p.flag_peer[p.rank] + kMaxWorld + peer) >= p.epoch; },
+                   "peers to finish reading");
+      }
+    }
+    return;
+  }
+
+  // =========================== compute CTAs ============================================
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int cta = blockIdx.x - p.n_copy, num_ctas = gridDim.x - p.n_copy;
+  constexpr uint32_t kTmemCols = 512;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b_local);
+    tma_prefetch_desc(&tma_b_gathered);
+    tma_prefetch_desc(&tma_c);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_ptr_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // tile -> (m_blk, n_blk): n-major, rotated so the local shard's column blocks come first
+  auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
+    const int n_idx = tile / p.num_m_blocks;
+    m_blk = tile - n_idx * p.num_m_blocks;
+    n_blk = first_local_blk + n_idx;
+    if (n_blk >= p.num_n_blocks) n_blk -= p.num_n_blocks;
+  };
+
+  if (warp_idx == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int ready_blk = -1;
+      for (int tile = cta; tile < num_tiles; tile += num_ctas) {
+        int m_blk, n_blk;
+        tile_coords(tile, m_blk, n_blk);
+        const bool local = n_blk >= first_local_blk && n_blk < first_local_blk + p.blocks_per_shard;
+        if (!local && ready_blk != n_blk) {
+          spin_until([&] { return ld_acquire_gpu(p.ready + n_blk) != 0u; }, "gathered weight block");
+          asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy copy -> async-proxy (TMA) reads
+          ready_blk = n_blk;
+        }
+        const CUtensorMap* mb = local ? &tma_b_local : &tma_b_gathered;
+        const int nb0 = local ? (n_blk - first_local_blk) * BLOCK_N : n_blk * BLOCK_N;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+          tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(sa + kABytes, mb, &full_bar[stage], kb * BLOCK_K, nb0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kFmtBF16, kFmtBF16, 0, 0, BLOCK_M, BLOCK_N);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int tile = cta; tile < num_tiles; tile += num_ctas) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_f16_ss(tmem_d, make_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024),
+                        make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[as]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else if (warp_idx >= kEpiWarpBase) {
+    const int q = warp_idx - kEpiWarpBase;
+    uint8_t* out_stage = smem + kOutOffset + q * 8192;
+    int obuf = 0, as = 0;
+    uint32_t aphase = 0;
+    for (int tile = cta; tile < num_tiles; tile += num_ctas) {
+      int m_blk, n_blk;
+      tile_coords(tile, m_blk, n_blk);
+      const int row0 = m_blk * BLOCK_M + q * 32, n0 = n_blk * BLOCK_N;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 64; ++c) {
+        const int col0 = n0 + c * 64;
+        if (col0 >= p.N) break;
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(taddr + c * 64, r0);
+        tmem_ld_32x32b_x32(taddr + c * 64 + 32, r1);
+        uint4 bias_v[8];
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            bias_v[j] = (col0 + j * 8 + 8 <= p.N) ? __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + j * 8))
+                                                  : make_uint4(0, 0, 0, 0);
+        }
+        tmem_ld_wait();
+        if (c == BLOCK_N / 64 - 1 || col0 + 64 >= p.N) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+        float v[64];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] = __uint_as_float(r0[i]);
+          v[32 + i] = __uint_as_float(r1[i]);
+        }
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float2 a = unpack_bf16x2(bias_v[j].x), b = unpack_bf16x2(bias_v[j].y),
+                   cc = unpack_bf16x2(bias_v[j].z), d = unpack_bf16x2(bias_v[j].w);
+            v[j * 8 + 0] += a.x; v[j * 8 + 1] += a.y; v[j * 8 + 2] += b.x; v[j * 8 + 3] += b.y;
+            v[j * 8 + 4] += cc.x; v[j * 8 + 5] += cc.y; v[j * 8 + 6] += d.x; v[j * 8 + 7] += d.y;
+          }
+        }
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        uint8_t* buf = out_stage + obuf * 4096 + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(buf + ((j ^ (lane & 7)) << 4)) =
+              make_uint4(pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                         pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tma_c, out_stage + obuf * 4096, col0, row0);
+          tma_store_commit();
+        }
+        obuf ^= 1;
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t bi,
+             uint32_t bo) {
+  PFN_encodeTiled enc = encode_fn();
+  if (!enc) return -100;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {bi, bo};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -200 - static_cast<int>(r);
+}
+
+}  // namespace
+
+// x [M, K] bf16 (row stride ldx), y [M, N] bf16 (row stride ldy). shard_ptrs: `world` peer-mapped pointers to
+// the [N/world, K] weight shards (dense, row stride K); gathered: local [N, K] scratch; ready: num_n_blocks
+// uint32 (this call zeroes them on `stream`); flag_ptrs: `world` symmetric buffers of >= 16 zeroed uint32;
+// local_sync: 2 zeroed uint32. Requirements: (N / world) % 256 == 0, K % 8 == 0.
+extern "C" int mg_ag_gemm(const void* x, void* y, const void* bias, const unsigned long long* shard_ptrs,
+                          void* gathered, void* ready, const unsigned long long* flag_ptrs, void* local_sync,
+                          int M, int N, int K, long long ldx, long long ldy, int rank, int world, int n_copy,
+                          unsigned int epoch, void* stream) {
+  if (world < 1 || world > kMaxWorld || N % world != 0 || (N / world) % BLOCK_N != 0 || K % 8 != 0) return -1;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  AgParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_blocks = N / BLOCK_N;
+  p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  for (int r = 0; r < kMaxWorld; ++r) {
+    p.shard_peer[r] = r < world ? reinterpret_cast<const __nv_bfloat16*>(shard_ptrs[r]) : nullptr;
+    p.flag_peer[r] = r < world ? reinterpret_cast<uint32_t*>(flag_ptrs[r]) : nullptr;
+  }
+  p.gathered = reinterpret_cast<__nv_bfloat16*>(gathered);
+  p.ready = reinterpret_cast<uint32_t*>(ready);
+  p.local_sync = reinterpret_cast<uint32_t*>(local_sync);
+  p.rank = rank; p.world = world;
+  p.blocks_per_shard = (N / world) / BLOCK_N;
+  p.epoch = epoch;
+  if (n_copy <= 0) n_copy = world > 1 ? 8 : 1;
+  p.n_copy = n_copy;
+
+  CUtensorMap ma, mbl, mbg, mc;
+  int rc = make_map(&ma, x, K, M, ldx, BLOCK_K, BLOCK_M);
+  if (rc) return rc;
+  rc = make_map(&mbl, reinterpret_cast<const void*>(shard_ptrs[rank]), K, N / world, K, BLOCK_K, BLOCK_N);
+  if (rc) return rc - 1000;
+  rc = make_map(&mbg, gathered, K, N, K, BLOCK_K, BLOCK_N);
+  if (rc) return rc - 2000;
+  rc = make_map(&mc, y, N, M, ldy, 64, 32);
+  if (rc) return rc - 3000;
+
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  constexpr int smem_bytes = kSmemTotal + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ag_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return -300 - static_cast<int>(e);
+    configured = true;
+  }
+  cudaMemsetAsync(ready, 0, sizeof(uint32_t) * p.num_n_blocks, s);
+  int tiles = p.num_m_blocks * p.num_n_blocks;
+  int compute = tiles < sms - n_copy ? tiles : sms - n_copy;
+  ag_gemm_kernel<<<n_copy + compute, kNumThreads, smem_bytes, s>>>(ma, mbl, mbg, mc, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
+}

@@ -522,8 +522,20 @@ int launch(const Maps& m, const GemmParams& p, int max_ctas, cudaStream_t stream
   }
   int units = p.num_m_blocks * p.num_n_blocks * p.splits;
   int grid = units < max_ctas ? units : max_ctas;
+  cudaError_t stale = cudaGetLastError();  // do not blame this launch for an older, unchecked error
+  if (stale != cudaSuccess)
+    fprintf(stderr, "maggy_b200 gemm: clearing stale CUDA error before launch: %s\n", cudaGetErrorString(stale));
   kern<<<grid, kNumThreads, smem_bytes, stream>>>(m.a, m.b, m.c, m.aux, p);
   cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    int dev = -1;
+    cudaGetDevice(&dev);
+    fprintf(stderr,
+            "maggy_b200 gemm: launch failed: %s (BN=%d stages=%d A=%d B=%d grid=%d smem=%d M=%d N=%d K=%d "
+            "splits=%d dev=%d stream=%p)\n",
+            cudaGetErrorString(e), BLOCK_N, STAGES, A_MAJOR, B_MAJOR, grid, smem_bytes, p.M, p.N, p.K, p.splits,
+            dev, static_cast<void*>(stream));
+  }
   return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
 }
 
@@ -559,7 +571,10 @@ int pick_block_n(int M, int N) {
     return waves * bn;
   };
   if (N < 256) return 192;
-  return cost(192) < cost(256) ? 192 : 256;
+  // Measured on B200 (profiles/gemm_bench_*.log): 192-wide tiles lose more to their lower arithmetic
+  // intensity (L2 -> smem traffic per FLOP) than they gain from the better last wave, even at N = 768, so
+  // 256 stays the default and 192 is only taken when it saves more than a quarter of the work units.
+  return cost(192) * 4 < cost(256) * 3 ? 192 : 256;
 }
 
 }  // namespace

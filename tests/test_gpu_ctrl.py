@@ -70,9 +70,15 @@ def test_persistent_scheduler_kernel_applies_median_rule():
 
     d = rpc.DriverChannel(2, ring_slots=64, pump=False)
     d.configure_policy(False, "max", 0, 1)     # host policy off: only the GPU kernel may stop trials
+    w0, w1 = rpc.WorkerChannel(d.name, 0), rpc.WorkerChannel(d.name, 1)
+    # In production the scheduler kernel lives in the driver process, which does no other CUDA work. Here the
+    # "worker" shares the process, so everything that allocates / maps (implicit device syncs would wait for
+    # the persistent kernel forever) happens BEFORE the kernel starts.
+    w1._device_state()
+    bad_metric = torch.tensor(0.1, device="cuda")
+    torch.cuda.synchronize()
     sched = DeviceScheduler(d, direction="max", es_min=0, es_interval=1, max_steps=32, cap_final=64)
     sched.start()
-    w0, w1 = rpc.WorkerChannel(d.name, 0), rpc.WorkerChannel(d.name, 1)
     good = Trial({"g": 1})
     for s in range(4):
         w0.post_metric(good.trial_id, 0.9, s)
@@ -80,7 +86,7 @@ def test_persistent_scheduler_kernel_applies_median_rule():
     time.sleep(0.2)
     bad = Trial({"b": 1})
     t_post = time.perf_counter()
-    w1.post_metric_device(bad.trial_id, torch.tensor(0.1, device="cuda"), 0)
+    w1.post_metric_device(bad.trial_id, bad_metric, 0)
     while not w1.check_stop(bad.trial_id):
         assert time.perf_counter() - t_post < 5.0, sched.stats()
     latency_ms = (time.perf_counter() - t_post) * 1e3

@@ -34,7 +34,7 @@ def test_gemm_kmajor(F, M, N, K, block_n):
 
 
 @pytest.mark.parametrize("a_major,b_major", [(0, 1), (1, 0), (1, 1)])
-@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (768, 3072, 4096), (520, 264, 1000)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (768, 3072, 4096), (520, 264, 1000), (128, 128, 1024)])
 def test_gemm_mn_major(F, a_major, b_major, M, N, K):
     torch.manual_seed(1)
     a = torch.randn(M, K, device=DEV, dtype=torch.bfloat16)

@@ -17,3 +17,13 @@ def test_fused_rs_adam_matches_nccl_oracle():
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "multi", "rs_adam_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0 and "RS_ADAM_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_allgather_fused_gemm():
+    import torch
+
+    n = min(torch.cuda.device_count(), 8)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "tests", "multi", "ag_gemm_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0 and "AG_GEMM_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
