@@ -186,6 +186,12 @@ class HyperparameterOptDriver(Driver):
         if self._controller_exhausted:
             self._maybe_finish()
             return
+        if self._lookahead_enabled and self._scheduled >= self.num_trials:
+            # model-based controllers count *finished* trials; with several workers that would overshoot
+            # num_trials by the number of trials in flight
+            self._controller_exhausted = True
+            self._maybe_finish()
+            return
         nxt = self._suggest(finished_trial)
         if nxt is None:
             self._controller_exhausted = True

@@ -287,6 +287,7 @@ class WorkerChannel:
             import torch
 
             cu = _lib.cuda()
+            cu.mg_set_device(torch.cuda.current_device())
             u64, P = ctypes.c_ulonglong, ctypes.c_void_p
             cu.mg_ring_map.argtypes, cu.mg_ring_map.restype = [P, u64], u64
             cu.mg_report_store.argtypes = [u64, u64, u64, ctypes.c_uint, P, ctypes.c_int, ctypes.c_longlong, u64,
@@ -310,6 +311,7 @@ class WorkerChannel:
         import torch
 
         d = self._device_state()
+        d["cu"].mg_set_device(torch.cuda.current_device())
         code = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2, torch.float64: 3}.get(tensor.dtype)
         if code is None:
             tensor, code = tensor.float(), 0
@@ -321,5 +323,16 @@ class WorkerChannel:
 
     def close(self):
         if self.h:
+            if self._dev is not None:
+                try:
+                    import torch
+
+                    torch.cuda.synchronize()
+                    cu = self._dev["cu"]
+                    cu.mg_ring_unmap.argtypes, cu.mg_ring_unmap.restype = [ctypes.c_void_p], ctypes.c_int
+                    cu.mg_ring_unmap(self.lib.mgr_base(self.h))
+                except Exception:
+                    pass
+                self._dev = None
             self.lib.mgr_close(self.h, 0)
             self.h = None

@@ -37,7 +37,8 @@ class DeviceScheduler:
         host = self.ch.lib
         h = self.ch.h
         with torch.cuda.device(self.device):
-            base = self.cu.mg_ring_map(host.mgr_base(h), host.mgr_bytes(h))
+            self._host_base = host.mgr_base(h)
+            base = self.cu.mg_ring_map(self._host_base, host.mgr_bytes(h))
             if not base:
                 raise RuntimeError("could not map the control segment into the CUDA address space")
             W = self.ch.num_workers
@@ -45,9 +46,7 @@ class DeviceScheduler:
             self.scratch = torch.zeros(nbytes + 64, dtype=torch.uint8, device=self.device)
             # quit flag lives in pinned host memory the kernel polls through its device mapping
             self.quit = torch.zeros(16, dtype=torch.int32).pin_memory()
-            quit_dev = self.cu.mg_ring_map(self.quit.data_ptr(), self.quit.numel() * 4)
-            if not quit_dev:
-                quit_dev = self.quit.data_ptr()  # pinned memory is UVA-addressable from the device
+            quit_dev = self.quit.data_ptr()  # torch-pinned memory is UVA-addressable from the device as is
             lo, _hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, 0)
             self.stream = torch.cuda.Stream(device=self.device, priority=0)
             u64 = self._u64
@@ -78,4 +77,8 @@ class DeviceScheduler:
             self.quit[0] = 1
             self.stream.synchronize()
             self.running = False
+            stats = self.stats()
+            self.cu.mg_ring_unmap.argtypes, self.cu.mg_ring_unmap.restype = [ctypes.c_void_p], ctypes.c_int
+            self.cu.mg_ring_unmap(self._host_base)  # never leave a registration behind an unmapped segment
+            return stats
         return self.stats()

@@ -28,6 +28,8 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kOutOffset = STAGES * kStageBytes;
 constexpr int kBarOffset = kOutOffset + 4 * 2 * 4096;
 constexpr int kSmemTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16;
+constexpr int kGatherChunk = 32768, kGatherStages = 6;  // 6 x 32 KB ring inside the (unused) operand stages
+static_assert(kGatherStages * kGatherChunk <= kOutOffset, "gather ring must fit in the operand stage area");
 
 struct AgParams {
   int M, N, K;
@@ -90,6 +92,15 @@ ag_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     const int remote_blocks = p.num_n_blocks - p.blocks_per_shard;
     const long long blk_elems = static_cast<long long>(BLOCK_N) * p.K;
+    uint64_t* gbar = reinterpret_cast<uint64_t*>(smem + kBarOffset);
+    uint32_t gphase[kGatherStages];
+#pragma unroll
+    for (int s = 0; s < kGatherStages; ++s) gphase[s] = 0;
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < kGatherStages; ++s) mbar_init(&gbar[s], 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
     for (int i = blockIdx.x; i < remote_blocks; i += p.n_copy) {
       // i-th remote block in "nearest shard first" order
       int n_blk = first_local_blk + p.blocks_per_shard + i;
@@ -98,22 +109,43 @@ ag_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if (threadIdx.x == 0)
         spin_until([&] { return ld_acquire_sys_u32(p.flag_peer[p.rank] + src) >= p.epoch; }, "peer shard");
       __syncthreads();
-      const uint4* sp = reinterpret_cast<const uint4*>(
+      const uint8_t* sp = reinterpret_cast<const uint8_t*>(
           p.shard_peer[src] + static_cast<long long>(n_blk - src * p.blocks_per_shard) * blk_elems);
-      uint4* dp = reinterpret_cast<uint4*>(p.gathered + static_cast<long long>(n_blk) * blk_elems);
-      const long long nvec = blk_elems >> 3;
-      long long v = threadIdx.x;
-      for (; v + 7 * kNumThreads < nvec; v += 8 * kNumThreads) {
-        uint4 r[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = ld_relaxed_sys_v4(sp + v + j * kNumThreads);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dp[v + j * kNumThreads] = r[j];
+      uint8_t* dp = reinterpret_cast<uint8_t*>(p.gathered + static_cast<long long>(n_blk) * blk_elems);
+      if (threadIdx.x == 0) {
+        // One thread drives a kGatherStages-deep ring of 32 KB bulk copies: peer HBM -> smem (mbarrier
+        // complete_tx) -> local HBM (bulk group). ~190 KB stay in flight per gather CTA, which is what it
+        // takes to hide the ~2-3 us NVLink round trip; 16-byte register loads cannot get there.
+        const long long blk_bytes = blk_elems * 2;
+        const int nchunks = static_cast<int>((blk_bytes + kGatherChunk - 1) / kGatherChunk);
+        auto chunk_bytes = [&](int c) {
+          long long left = blk_bytes - static_cast<long long>(c) * kGatherChunk;
+          return static_cast<uint32_t>(left < kGatherChunk ? left : kGatherChunk);
+        };
+        const int prefetch = nchunks < kGatherStages ? nchunks : kGatherStages;
+        for (int c = 0; c < prefetch; ++c) {
+          mbar_arrive_expect_tx(&gbar[c], chunk_bytes(c));
+          bulk_load_1d(smem + c * kGatherChunk, sp + static_cast<long long>(c) * kGatherChunk, chunk_bytes(c),
+                       &gbar[c]);
+        }
+        for (int c = 0; c < nchunks; ++c) {
+          const int s = c % kGatherStages;
+          mbar_wait(&gbar[s], gphase[s]);
+          gphase[s] ^= 1;
+          bulk_store_1d(dp + static_cast<long long>(c) * kGatherChunk, smem + s * kGatherChunk, chunk_bytes(c));
+          tma_store_commit();
+          if (c + kGatherStages < nchunks) {
+            tma_store_wait_read<0>();  // the store has finished reading this stage: refill it
+            const int cn = c + kGatherStages;
+            mbar_arrive_expect_tx(&gbar[s], chunk_bytes(cn));
+            bulk_load_1d(smem + s * kGatherChunk, sp + static_cast<long long>(cn) * kGatherChunk, chunk_bytes(cn),
+                         &gbar[s]);
+          }
+        }
+        tma_store_wait<0>();  // block fully written
+        __threadfence();
+        st_release_gpu(p.ready + n_blk, 1u);
       }
-      for (; v < nvec; v += kNumThreads) dp[v] = ld_relaxed_sys_v4(sp + v);
-      __threadfence();
-      __syncthreads();
-      if (threadIdx.x == 0) st_release_gpu(p.ready + n_blk, 1u);
     }
     // done reading peers: tell them, then (last gather CTA only) wait until everybody is done with MY shard
     __syncthreads();

@@ -214,11 +214,18 @@ extern "C" {
 // pointer (0 on failure). Safe to call once per process per segment.
 unsigned long long mg_ring_map(void* host_base, unsigned long long bytes) {
   cudaError_t e = cudaHostRegister(host_base, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
-  if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered) {
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    // A previous segment that lived at this virtual address was unmapped without being unregistered: the
+    // stale registration still points at its old physical pages. Drop it and register the new mapping.
+    cudaGetLastError();
+    cudaHostUnregister(host_base);
+    cudaGetLastError();
+    e = cudaHostRegister(host_base, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+  }
+  if (e != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
-  cudaGetLastError();
   void* dptr = nullptr;
   if (cudaHostGetDevicePointer(&dptr, host_base, 0) != cudaSuccess) return 0;
   return reinterpret_cast<unsigned long long>(dptr);

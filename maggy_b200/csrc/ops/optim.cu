@@ -122,3 +122,16 @@ extern "C" int mg_cast_f32_bf16(const float* src, void* dst, long long n, void* 
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
 }
+
+// Bind this library's (statically linked) CUDA runtime to device `dev` on the calling thread. PyTorch runs
+// backward on worker threads that may not have a driver context bound yet; driver-API entry points used
+// here (cuTensorMapEncodeTiled) need one, and on rank > 0 it must be the right device.
+extern "C" int mg_set_device(int dev) {
+  static thread_local int current = -1;
+  if (current == dev) return 0;
+  cudaError_t e = cudaSetDevice(dev);
+  if (e != cudaSuccess) return -400 - static_cast<int>(e);
+  cudaFree(nullptr);  // force context creation / binding on this thread
+  current = dev;
+  return 0;
+}

@@ -38,6 +38,9 @@ def _count(n: int = 1):
 
 
 def _stream() -> int:
+    """Current torch stream handle; also binds the kernel library's runtime to torch's current device on this
+    thread (autograd worker threads start without a bound driver context)."""
+    _lib.cuda().mg_set_device(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -90,6 +93,7 @@ def gemm(a, b, *, a_major=K_MAJOR, b_major=K_MAJOR, bias=None, aux=None, epi=EPI
     if bias is not None:
         assert bias.dtype == torch.bfloat16 and bias.numel() == N and bias.is_contiguous()
     lib = _lib.cuda()
+    stream = _stream()
     ws = None
     if splits is None:
         splits = 1
@@ -102,7 +106,7 @@ def gemm(a, b, *, a_major=K_MAJOR, b_major=K_MAJOR, bias=None, aux=None, epi=EPI
         a.data_ptr(), b.data_ptr(), out.data_ptr(), _ptr(bias), _ptr(aux), M, N, K,
         a.stride(0), b.stride(0), out.stride(0), ld_aux, a_major, b_major, epi,
         1 if out.dtype == torch.float32 else 0, 1 if accumulate else 0, block_n, sm_limit, splits,
-        _ptr(ws), _stream())
+        _ptr(ws), stream)
     _lib.check(rc, f"mg_gemm_bf16(M={M},N={N},K={K})")
     _count(2 if splits > 1 else 1)
     return out

@@ -212,7 +212,7 @@ class FusedAdamW:
                 self.eps, self.weight_decay, self.step_count, self.grad_scale,
                 0 if gn is None else gn.data_ptr(), self.max_grad_norm,
                 0 if st is None else st.data_ptr(), 0 if lt is None else lt.data_ptr(), self.num_ctas,
-                torch.cuda.current_stream().cuda_stream)
+                F._stream())
             _lib.check(rc, "mg_rs_adam")
             F._count(1)
         flat.start_step()

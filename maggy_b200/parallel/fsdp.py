@@ -75,7 +75,7 @@ def ag_linear(x: torch.Tensor, w: ShardedWeight, bias: Optional[torch.Tensor] = 
     rc = _lib.cuda().mg_ag_gemm(x2.data_ptr(), out.data_ptr(), 0 if bias is None else bias.data_ptr(), w._shard_ptrs,
                                 w.gathered.data_ptr(), w.ready.data_ptr(), w._flag_ptrs, w.local_sync.data_ptr(),
                                 M, w.rows, K, x2.stride(0), out.stride(0), w.rank, w.world, w.n_copy, w.epoch,
-                                torch.cuda.current_stream().cuda_stream)
+                                F._stream())
     _lib.check(rc, "mg_ag_gemm")
     F._count(1)
     return out.view(*x.shape[:-1], w.rows)

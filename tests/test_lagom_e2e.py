@@ -285,3 +285,34 @@ def test_torch_distributed_training_over_gloo():
     run = _run_dir()
     assert os.path.exists(os.path.join(run, "training_logs_0", "output.log"))
     assert os.path.exists(os.path.join(run, "training_logs_1", ".outputs.json"))
+
+
+def train_gang(hparams, reporter):
+    import torch
+    import torch.distributed as dist
+
+    assert dist.is_initialized() and dist.get_world_size() == 2
+    t = torch.tensor([float(dist.get_rank() + 1)])
+    dist.all_reduce(t)                       # both gang members run the same trial
+    for i in range(2):
+        reporter.broadcast(hparams["x"] + t.item(), i)
+    return hparams["x"] + float(dist.get_rank())   # leader reports the gang mean
+
+
+def test_multi_process_trial_gangs(monkeypatch):
+    """gpus_per_trial=2: every trial runs on a 2-process gang with a ready process group (gloo on CPU)."""
+    monkeypatch.setenv("MAGGY_NUM_EXECUTORS", "4")
+    sp = Searchspace(x=("DOUBLE", [0.0, 1.0]))
+    cfg = HyperparameterOptConfig(num_trials=4, optimizer="randomsearch", searchspace=sp, direction="max",
+                                  es_policy="none", name="gang", gpus_per_trial=2, seed=5)
+    res = experiment.lagom(train_gang, cfg)
+    assert res["num_trials"] == 4
+    run = _run_dir()
+    meta = json.load(open(os.path.join(run, "maggy.json")))
+    assert meta["executors"] == 2          # 4 processes = 2 gangs of 2
+    for tid in os.listdir(run):
+        p = os.path.join(run, tid, "trial.json")
+        if os.path.exists(p):
+            t = json.load(open(p))
+            assert t["final_metric"] == pytest.approx(t["params"]["x"] + 0.5)      # mean of x+0 and x+1
+            assert t["metric_history"] == pytest.approx([t["params"]["x"] + 3.0] * 2)
