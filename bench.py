@@ -37,7 +37,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=32, help="sequences per GPU per step")
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-multicast", action="store_true")
+    ap.add_argument("--no-multicast", action="store_true", help="force the peer load/store variant of the fused kernel")
+    ap.add_argument("--multicast", action="store_true", help="force the NVSwitch multimem variant (default: auto)")
     return ap.parse_args()
 
 
@@ -147,7 +148,7 @@ def main():
 
         model, flat, opt, step = build_gpt2_trainer(
             cfg, B, T, device, world_size=world, rank=rank, use_cuda_graph=not args.no_graph,
-            use_multicast=not args.no_multicast)
+            use_multicast=False if args.no_multicast else (True if args.multicast else "auto"))
         uses_mc = opt.uses_multicast
     else:
         step, uses_mc = build_torch_baseline(cfg, B, T, device, world, rank)

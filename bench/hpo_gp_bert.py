@@ -34,7 +34,7 @@ def make_train_fn(model_name, batch, seq, steps, cpu):
             return -loss
         from maggy_b200.parallel.data_parallel import DataParallel
 
-        dev = torch.device("cuda", 0)
+        dev = torch.device("cuda", torch.cuda.current_device())
         model = DataParallel(BertForMaskedLM(cfg), device=dev) if dist.is_initialized() else None
         if model is None:
             from maggy_b200.parallel.arena import FlatParams, FusedAdamW

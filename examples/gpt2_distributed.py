@@ -16,7 +16,7 @@ def train_fn(module, hparams, reporter):
     cfg = GPT2Config.named(hparams["model"])
     model = module(cfg)                                   # built, sharded and wrapped by the framework
     opt = torch.optim.AdamW(model.parameters(), lr=hparams["lr"], weight_decay=0.1)   # -> FusedAdamW under zero_lvl>=1
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", torch.cuda.current_device())
     g = torch.Generator().manual_seed(int(os.environ.get("RANK", "0")))
     loss = None
     for step in range(hparams["steps"]):

@@ -140,7 +140,8 @@ class Driver(ABC):
         with open(spec_path, "wb") as f:
             cloudpickle.dump(spec, f)
         self.pool = WorkerPool(self.num_executors, self.channel.name, spec_path, self.log_dir,
-                               gpus_per_worker=self.gpus_per_worker)
+                               gpus_per_worker=self.gpus_per_worker,
+                               share_devices=getattr(self, "share_devices", False))
         self.pool.start()
 
     # ------------------------------------------------------------------ supervision (main thread)

@@ -23,6 +23,7 @@ RUN_ID64 = "00000000000000d1"
 class TorchDistributedTrainingDriver(Driver):
     executor_kind = "torch_dist"
     experiment_type = "torch_dist"
+    share_devices = True   # one collective job: every rank must see every GPU (symmetric memory / P2P)
 
     def __init__(self, config, app_id, run_id):
         super().__init__(config, app_id, run_id)

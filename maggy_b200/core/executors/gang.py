@@ -18,15 +18,16 @@ class Gang:
         import torch.distributed as dist
 
         self.rank, self.size = rank, size
+        local = int(os.environ.get("MAGGY_LOCAL_RANK", "0"))
         os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank),
-                           "WORLD_SIZE": str(size), "LOCAL_RANK": "0"})
+                           "WORLD_SIZE": str(size), "LOCAL_RANK": str(local)})
         use_cuda = torch.cuda.is_available()
         if use_cuda:
-            torch.cuda.set_device(0)  # CUDA_VISIBLE_DEVICES already pins this process to its GPU
+            torch.cuda.set_device(local)  # the gang sees its own GPUs; member r drives cuda:r
         dist.init_process_group("nccl" if use_cuda else "gloo", rank=rank, world_size=size,
                                 timeout=datetime.timedelta(seconds=timeout_s))
         self.dist = dist
-        self.device = torch.device("cuda", 0) if use_cuda else torch.device("cpu")
+        self.device = torch.device("cuda", local) if use_cuda else torch.device("cpu")
 
     @property
     def is_leader(self) -> bool:

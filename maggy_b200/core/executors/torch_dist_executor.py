@@ -26,11 +26,12 @@ def _init_cluster(rank, world, addr, port, timeout_s=60):
     import torch
     import torch.distributed as dist
 
+    local = int(os.environ.get("MAGGY_LOCAL_RANK", "0"))
     os.environ.update({"MASTER_ADDR": addr, "MASTER_PORT": str(port), "WORLD_SIZE": str(world), "RANK": str(rank),
-                       "LOCAL_RANK": "0"})
+                       "LOCAL_RANK": str(local)})
     use_cuda = torch.cuda.is_available()
     if use_cuda:
-        torch.cuda.set_device(0)  # CUDA_VISIBLE_DEVICES pins this process to its GPU
+        torch.cuda.set_device(local)  # all ranks see all GPUs (peer-mapped symmetric memory), each drives its own
     if world > 1 or True:
         dist.init_process_group("nccl" if use_cuda else "gloo", rank=rank, world_size=world,
                                 timeout=datetime.timedelta(seconds=timeout_s))

@@ -51,7 +51,8 @@ def free_port() -> int:
 
 class WorkerPool:
     def __init__(self, num_workers: int, segment: str, spec_path: str, log_dir: str,
-                 gpus_per_worker: int = 1, use_gpus: Optional[bool] = None, extra_env: Optional[Dict[str, str]] = None):
+                 gpus_per_worker: int = 1, use_gpus: Optional[bool] = None, extra_env: Optional[Dict[str, str]] = None,
+                 share_devices: bool = False):
         from .. import util
 
         self.lib = _launcher()
@@ -65,6 +66,9 @@ class WorkerPool:
         self.ports = [free_port() for _ in range(num_workers)]
         self.extra_env = dict(extra_env or {})
         self.ncpu = os.cpu_count() or 1
+        # share_devices: every worker sees ALL pool GPUs and selects its own by MAGGY_LOCAL_RANK (needed when
+        # the workers form one collective job: peer-mapped symmetric memory wants distinct device indices)
+        self.share_devices = share_devices
 
     def _slot(self, worker: int, rank: int) -> int:
         return worker * self.gang + rank
@@ -87,7 +91,16 @@ class WorkerPool:
             env = {"PYTHONPATH": os.pathsep.join(dict.fromkeys(paths)), "MAGGY_WORKER_ID": str(worker),
                    "PYTHONUNBUFFERED": "1"}
             env.update(self.extra_env)
-            gpus = str(slot) if self.use_gpus else "-1"
+            if not self.use_gpus:
+                gpus, local_rank = "-1", 0
+            elif self.share_devices:
+                gpus, local_rank = ",".join(str(i) for i in range(self.num_workers * self.gang)), slot
+            elif self.gang > 1:
+                # a gang sees exactly its own GPUs; rank r of the gang uses cuda:r
+                gpus, local_rank = ",".join(str(worker * self.gang + r) for r in range(self.gang)), rank
+            else:
+                gpus, local_rank = str(slot), 0
+            env["MAGGY_LOCAL_RANK"] = str(local_rank)
             log = os.path.join(self.log_dir, f"worker_{worker}_{rank}.stdout.log")
             rc = self.lib.mgl_spawn(self.pool, slot, _blob(argv), _blob([f"{k}={v}" for k, v in env.items()]),
                                     gpus.encode(), (slot * cpus_per) % self.ncpu, cpus_per, log.encode())

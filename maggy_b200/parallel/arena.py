@@ -130,7 +130,7 @@ class FusedAdamW:
     """
 
     def __init__(self, flat: FlatParams, lr=3e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1,
-                 grad_scale: Optional[float] = None, max_grad_norm: float = 0.0, use_multicast=True,
+                 grad_scale: Optional[float] = None, max_grad_norm: float = 0.0, use_multicast="auto",
                  num_ctas: int = 0):
         self.flat = flat
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
@@ -158,6 +158,14 @@ class FusedAdamW:
             self._grad_ptrs = arr(*flat.peer_ptrs("grads"))
             self._param_ptrs = arr(*flat.peer_ptrs("params"))
             self._flag_ptrs = arr(*flat.peer_ptrs("flags"))
+            if use_multicast == "auto":
+                # measured (profiles/k1_roofline_*.json): at 2 ranks direct peer loads/stores beat the
+                # NVSwitch multicast path (0.43 vs 0.65 ms on the GPT-2 small arena); in-switch reduction pays
+                # off once a rank would otherwise pull from many peers
+                import os
+
+                env = os.environ.get("MAGGY_B200_MULTICAST")
+                use_multicast = (env == "1") if env in ("0", "1") else W >= 4
             self._grad_mc = flat.multicast_ptr("grads") if use_multicast else 0
             self._param_mc = flat.multicast_ptr("params") if use_multicast else 0
             _lib.register_cuda_symbol(

@@ -83,7 +83,7 @@ class TrainStep:
 
 def build_gpt2_trainer(cfg, batch_size: int, seq_len: int, device, world_size: int = 1, rank: int = 0,
                        group=None, lr: float = 3e-4, weight_decay: float = 0.1, use_cuda_graph: bool = True,
-                       use_multicast: bool = True, seed: int = 1234):
+                       use_multicast="auto", seed: int = 1234):
     """Public convenience constructor used by bench.py / smoke(): GPT-2 + arena + fused AdamW + graph."""
     from ..models.gpt2 import GPT2
 

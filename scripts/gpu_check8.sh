@@ -6,7 +6,7 @@ run() { timeout -k 10 $1 python -m torch.distributed.run --nnodes=1 --nproc-per-
 run 200 29601 tests/multi/rs_adam_check.py > gpurun_out/rs_adam_check_n$N.log 2>&1
 run 200 29602 tests/multi/ag_gemm_check.py > gpurun_out/ag_gemm_check_n$N.log 2>&1
 run 200 29603 bench/k1_roofline.py > gpurun_out/k1_roofline_n$N.log 2>&1
-NCCL_DEBUG=INFO run 240 29604 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.log 2>&1
+NCCL_DEBUG=INFO run 240 29604 bench.py --gpus $N --steps 20 --warmup 5 --multicast > gpurun_out/bench_n$N.log 2>&1
 run 240 29605 bench.py --gpus $N --steps 20 --warmup 5 --no-multicast > gpurun_out/bench_n${N}_nomc.log 2>&1
 run 240 29606 bench.py --gpus $N --steps 10 --warmup 3 --impl torch > gpurun_out/bench_n${N}_torch.log 2>&1
 timeout -k 10 420 python bench/hpo_asha_resnet.py --workers $N --trials 32 --steps-per-budget 10 --batch 64 > gpurun_out/hpo_asha_n$N.log 2>&1
