@@ -39,6 +39,43 @@ class Gang:
         self.dist.broadcast_object_list(box, src=0, device=self.device)
         return box[0]
 
+    def reset_agreement(self):
+        self._pending = None
+
+    def agree_stop(self, local_flag: bool) -> bool:
+        """Collective OR of the members' stop flags with a one-call delay: returns the OR of the flags passed
+        at the PREVIOUS call, so every member sees the same answer at the same call index, and the host never
+        waits for more than the previous call's (long finished) all-reduce."""
+        import torch
+
+        prev = False
+        pend = getattr(self, "_pending", None)
+        if pend is not None:
+            done, host = pend
+            if done is not None:
+                done.synchronize()
+            prev = bool(int(host[0]) != 0)
+        if self.device.type == "cuda":
+            if not hasattr(self, "_side"):
+                self._side = torch.cuda.Stream(device=self.device)
+            flag = torch.full((1,), 1 if local_flag else 0, dtype=torch.int32, device=self.device)
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX)
+            ready = torch.cuda.Event()
+            ready.record()
+            host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(ready)
+                host.copy_(flag, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record()
+            flag.record_stream(self._side)
+            self._pending = (done, host)
+        else:
+            flag = torch.tensor([1 if local_flag else 0], dtype=torch.int32)
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX)
+            self._pending = (None, flag)
+        return prev
+
     def mean(self, value: float) -> float:
         import torch
 

@@ -72,6 +72,9 @@ def run_one_trial(spec, trial_id, params, reporter, log_dir, gang=None):
             env.mkdir(trial_dir)
         reporter.init_logger(trial_log)
     tensorboard._register(trial_dir)
+    if gang is not None:
+        reporter.gang = gang
+        gang.reset_agreement()
     hparams = dict(params)
     if spec["experiment_type"] == "ablation":
         printable = {k: hparams.pop(k) for k in ("ablated_feature", "ablated_layer") if k in hparams}

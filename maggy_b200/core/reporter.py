@@ -44,6 +44,9 @@ class Reporter:
         # heartbeat thread calling ship() once per hb_interval, and STOP arrives with that heartbeat
         self.deferred = False
         self._shipped_step = None
+        # multi-GPU trial gangs: only the leader hears STOP from the driver, but every member must leave
+        # train_fn at the same broadcast() call or the others hang in their next collective
+        self.gang = None
         env = EnvSing.get_instance()
         if log_file:
             if not env.exists(log_file):
@@ -101,7 +104,12 @@ class Reporter:
                 if not self.stop and self.channel.check_stop(self.trial_id):
                     self.stop = True
                 self._maybe_flush_logs()
-            if self.stop:
+            if self.gang is not None:
+                # agreement is reached one call later: all members raise at the same call index
+                if self.gang.agree_stop(self.stop):
+                    self.stop = True
+                    raise exceptions.EarlyStopException(self._metric_value())
+            elif self.stop:
                 raise exceptions.EarlyStopException(self._metric_value())
 
     def ship(self):

@@ -60,6 +60,24 @@ MG_DEVICE void multimem_st_v4(void* mc_addr, const uint4& v) {
                : "memory");
 }
 
+// Bounded spin: a rank that never arrives (crashed peer, early-stopped gang member) must surface as a
+// launch failure on the waiting ranks, not as a GPU that spins forever.
+template <class Pred>
+MG_DEVICE void spin_until(Pred ready, const char* what) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!ready()) {
+    if ((++spins & 0x3FF) == 0) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) {
+        printf("maggy_b200 rs_adam: timed out waiting for %s (block %d)\n", what, static_cast<int>(blockIdx.x));
+        __trap();
+      }
+    }
+  }
+}
+
 // All ranks rendezvous: block 0 signals every peer, waits for every peer, then releases the local CTAs.
 MG_DEVICE void begin_barrier(const RsAdamArgs& a) {
   if (blockIdx.x == 0) {
@@ -67,8 +85,7 @@ MG_DEVICE void begin_barrier(const RsAdamArgs& a) {
       const int peer = threadIdx.x;
       __threadfence_system();
       st_release_sys_u32(a.flag_peer[peer] + a.rank, a.epoch);
-      while (ld_acquire_sys_u32(a.flag_peer[a.rank] + peer) < a.epoch) {
-      }
+      spin_until([&] { return ld_acquire_sys_u32(a.flag_peer[a.rank] + peer) >= a.epoch; }, "peer gradients");
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -76,10 +93,11 @@ MG_DEVICE void begin_barrier(const RsAdamArgs& a) {
     }
   } else {
     if (threadIdx.x == 0) {
-      uint32_t v;
-      do {
+      spin_until([&] {
+        uint32_t v;
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.local_sync) : "memory");
-      } while (v < a.epoch);
+        return v >= a.epoch;
+      }, "local begin barrier");
     }
     __syncthreads();
   }
@@ -104,8 +122,8 @@ MG_DEVICE void end_barrier(const RsAdamArgs& a) {
       const int peer = threadIdx.x;
       __threadfence_system();
       st_release_sys_u32(a.flag_peer[peer] + kMaxWorld + a.rank, a.epoch);
-      while (ld_acquire_sys_u32(a.flag_peer[a.rank] + kMaxWorld + peer) < a.epoch) {
-      }
+      spin_until([&] { return ld_acquire_sys_u32(a.flag_peer[a.rank] + kMaxWorld + peer) >= a.epoch; },
+                 "peers to finish writing parameters");
     }
     __syncthreads();
   }

@@ -55,7 +55,8 @@ def test_gemm_uses_tcgen05_tmem_and_tma(sass):
 def test_allgather_gemm_mixes_peer_loads_with_tensor_core_tiles(sass):
     (text,) = _kernels(sass, "ag_gemm_kernel").values()
     assert "UTCHMMA" in text and "UTMALDG" in text and "UTMASTG" in text
-    assert re.search(r"LDG\.E\.128\.STRONG\.SYS", text)           # peer-memory loads in the same kernel
+    assert "UBLKCP.S.G" in text and "UBLKCP.G.S" in text          # bulk copies: peer HBM -> smem -> local HBM
+    assert re.search(r"(LDG|STG)\.E(\.\d+)?\.STRONG\.SYS", text)    # cross-GPU ready / done flags
 
 
 def test_fused_reduce_scatter_adam_uses_multimem_and_sys_scope(sass):

@@ -316,3 +316,26 @@ def test_multi_process_trial_gangs(monkeypatch):
             t = json.load(open(p))
             assert t["final_metric"] == pytest.approx(t["params"]["x"] + 0.5)      # mean of x+0 and x+1
             assert t["metric_history"] == pytest.approx([t["params"]["x"] + 3.0] * 2)
+
+
+def train_gang_early_stop(hparams, reporter):
+    import torch
+    import torch.distributed as dist
+
+    for i in range(100):
+        t = torch.ones(1)
+        dist.all_reduce(t)                    # a member that left early would dead-lock the other one here
+        reporter.broadcast(hparams["q"], i)
+        import time
+
+        time.sleep(0.003)
+    return hparams["q"]
+
+
+def test_gang_members_stop_together(monkeypatch):
+    monkeypatch.setenv("MAGGY_NUM_EXECUTORS", "2")
+    sp = Searchspace(q=("DOUBLE", [0.0, 1.0]))
+    cfg = HyperparameterOptConfig(num_trials=8, optimizer="randomsearch", searchspace=sp, direction="max",
+                                  es_policy="median", es_interval=1, es_min=2, name="gang_es", gpus_per_trial=2, seed=2)
+    res = experiment.lagom(train_gang_early_stop, cfg)
+    assert res["num_trials"] == 8 and res["early_stopped"] >= 1
