@@ -113,7 +113,8 @@ def reference_arm(args):
     if why is None:
         why = ("reference imports but its torch-distributed driver needs a Spark cluster "
                "(pyspark) and is broken as written (_patching_fn arity, SURVEY.md 2.8)")
-    print(json.dumps({"impl": "reference", "unavailable": why}))
+    if int(os.environ.get("RANK", "0")) == 0:  # under torchrun every rank gets here: one line only
+        print(json.dumps({"impl": "reference", "unavailable": why}))
     return 0
 
 

@@ -35,9 +35,13 @@ class Gang:
 
     def broadcast(self, obj):
         """Leader -> followers object broadcast (trial assignment, stop sentinel)."""
-        box = [obj]
+        import cloudpickle
+
+        # trial payloads may carry closures (ablation model/dataset generators): cloudpickle them ourselves,
+        # torch's object collectives use the plain pickler
+        box = [cloudpickle.dumps(obj) if self.rank == 0 else None]
         self.dist.broadcast_object_list(box, src=0, device=self.device)
-        return box[0]
+        return cloudpickle.loads(box[0])
 
     def reset_agreement(self):
         self._pending = None

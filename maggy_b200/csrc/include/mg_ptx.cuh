@@ -118,6 +118,23 @@ MG_DEVICE void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar
       : "memory");
 }
 
+// Multicast variant: the box lands at the same shared-memory offset in every CTA of `cta_mask` and completes
+// `bytes` on the mbarrier at the same offset in each of them.
+MG_DEVICE void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1,
+                              uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
+      "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+
+MG_DEVICE void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 MG_DEVICE void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0,
                                 int32_t c1, uint64_t cache_hint) {
   asm volatile(
@@ -219,6 +236,14 @@ MG_DEVICE void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
+}
+
+// Same, but the arrive is multicast to the barrier at this offset in every CTA of `cta_mask`.
+MG_DEVICE void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
 }
 
 // 32 lanes x 32 columns of fp32: thread t of the warp receives row (lane base + t).

@@ -17,6 +17,7 @@
 #include "../include/mg_ptx.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 namespace {
@@ -88,7 +89,10 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
                     pack_bf16x2(v[6], v[7]));
 }
 
-template <int BLOCK_N, int STAGES, int A_MAJOR, int B_MAJOR>
+// MC = true: thread-block clusters of 2 CTAs that work on vertically adjacent output tiles (same n-block,
+// m-blocks 2i and 2i+1). Each CTA fetches only HALF of the shared B tile and TMA-multicasts it into both
+// CTAs' shared memory, which cuts the L2 -> smem operand traffic per CTA from 48 KB to 32 KB per k-block.
+template <int BLOCK_N, int STAGES, int A_MAJOR, int B_MAJOR, bool MC>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                          const __grid_constant__ CUtensorMap tma_b,
@@ -107,8 +111,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  uint32_t crank = 0;
+  if constexpr (MC) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  // iteration domain: one work unit per CTA (MC = false) or per CTA pair (MC = true)
+  const int m_groups = MC ? (p.num_m_blocks + 1) / 2 : p.num_m_blocks;
+  const int num_tiles = m_groups * p.num_n_blocks;
   const int num_units = num_tiles * p.splits;
+  const int unit_begin = MC ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int unit_step = MC ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  auto coords = [&](int tile, int& m_blk, int& n_blk) {
+    int mg;
+    tile_coords(tile, m_groups, p.num_n_blocks, mg, n_blk);
+    m_blk = MC ? mg * 2 + static_cast<int>(crank) : mg;
+  };
   constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 256) ? 256 : 512;  // allocation must be a power of two
 
   if (warp_idx == 0 && lane == 0) {
@@ -122,7 +137,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC ? 2 : 1);  // MC: the peer multicasts into this stage too
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -136,6 +151,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync();  // peer barriers must be initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -144,10 +160,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      for (int unit = unit_begin; unit < num_units; unit += unit_step) {
         const int tile = unit % num_tiles, split = unit / num_tiles;
         int m_blk, n_blk;
-        tile_coords(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
+        coords(tile, m_blk, n_blk);
         const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
@@ -164,12 +180,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
             for (int c = 0; c < BLOCK_M / 64; ++c)
               tma_load_2d(sa + c * (BLOCK_K * 128), &tma_a, &full_bar[stage], m0 + c * 64, k0);
           }
-          if constexpr (B_MAJOR == 0) {
-            tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);
-          } else {
+          if constexpr (!MC) {
+            if constexpr (B_MAJOR == 0) {
+              tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BLOCK_N / 64; ++c)
-              tma_load_2d(sb + c * (BLOCK_K * 128), &tma_b, &full_bar[stage], n0 + c * 64, k0);
+              for (int c = 0; c < BLOCK_N / 64; ++c)
+                tma_load_2d(sb + c * (BLOCK_K * 128), &tma_b, &full_bar[stage], n0 + c * 64, k0);
+            }
+          } else {
+            // my half of the B tile, delivered to both CTAs of the cluster (same smem offset, same barrier)
+            if constexpr (B_MAJOR == 0) {
+              tma_load_2d_mc(sb + crank * (L::kBBytes / 2), &tma_b, &full_bar[stage], k0,
+                             n0 + static_cast<int>(crank) * (BLOCK_N / 2), 0x3);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BLOCK_N / 128; ++c) {
+                const int cc = static_cast<int>(crank) * (BLOCK_N / 128) + c;
+                tma_load_2d_mc(sb + cc * (BLOCK_K * 128), &tma_b, &full_bar[stage], n0 + cc * 64, k0, 0x3);
+              }
+            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -186,7 +216,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      for (int unit = unit_begin; unit < num_units; unit += unit_step) {
         const int split = unit / num_tiles;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
@@ -211,7 +241,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                                     : make_smem_desc_sw128(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024);
             umma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if constexpr (MC) umma_commit_mc(&empty_bar[stage], 0x3);  // release the slot in BOTH CTAs
+          else umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
           if (++stage == STAGES) {
             stage = 0;
@@ -229,10 +260,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     int obuf = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+    for (int unit = unit_begin; unit < num_units; unit += unit_step) {
       const int tile = unit % num_tiles, split = unit / num_tiles;
       int m_blk, n_blk;
-      tile_coords(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
+      coords(tile, m_blk, n_blk);
       const int row0 = m_blk * BLOCK_M + q * 32;
       const int row = row0 + lane;
       const int n0 = n_blk * BLOCK_N;
@@ -428,6 +459,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync();  // nobody leaves while the peer may still multicast into / arrive on this CTA
   if (warp_idx == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -507,10 +539,10 @@ struct Maps {
   CUtensorMap a, b, c, aux;
 };
 
-template <int BLOCK_N, int STAGES, int A_MAJOR, int B_MAJOR>
+template <int BLOCK_N, int STAGES, int A_MAJOR, int B_MAJOR, bool MC>
 int launch(const Maps& m, const GemmParams& p, int max_ctas, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, STAGES>;
-  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, STAGES, A_MAJOR, B_MAJOR>;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, STAGES, A_MAJOR, B_MAJOR, MC>;
   constexpr int smem_bytes = L::kTotal + 1024;
   static_assert(smem_bytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
   static bool configured = false;
@@ -520,32 +552,57 @@ int launch(const Maps& m, const GemmParams& p, int max_ctas, cudaStream_t stream
     if (e != cudaSuccess) return -300 - static_cast<int>(e);
     configured = true;
   }
-  int units = p.num_m_blocks * p.num_n_blocks * p.splits;
-  int grid = units < max_ctas ? units : max_ctas;
+  const int m_groups = MC ? (p.num_m_blocks + 1) / 2 : p.num_m_blocks;
+  int units = m_groups * p.num_n_blocks * p.splits;
+  int grid;
+  if (MC) {
+    int clusters = max_ctas / 2;
+    grid = 2 * (units < clusters ? units : clusters);
+  } else {
+    grid = units < max_ctas ? units : max_ctas;
+  }
   cudaError_t stale = cudaGetLastError();  // do not blame this launch for an older, unchecked error
   if (stale != cudaSuccess)
     fprintf(stderr, "maggy_b200 gemm: clearing stale CUDA error before launch: %s\n", cudaGetErrorString(stale));
-  kern<<<grid, kNumThreads, smem_bytes, stream>>>(m.a, m.b, m.c, m.aux, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  if (MC) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, m.a, m.b, m.c, m.aux, p);
+    if (e == cudaSuccess) e = cudaGetLastError();
+  } else {
+    kern<<<grid, kNumThreads, smem_bytes, stream>>>(m.a, m.b, m.c, m.aux, p);
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess) {
     int dev = -1;
     cudaGetDevice(&dev);
     fprintf(stderr,
-            "maggy_b200 gemm: launch failed: %s (BN=%d stages=%d A=%d B=%d grid=%d smem=%d M=%d N=%d K=%d "
+            "maggy_b200 gemm: launch failed: %s (BN=%d stages=%d A=%d B=%d MC=%d grid=%d smem=%d M=%d N=%d K=%d "
             "splits=%d dev=%d stream=%p)\n",
-            cudaGetErrorString(e), BLOCK_N, STAGES, A_MAJOR, B_MAJOR, grid, smem_bytes, p.M, p.N, p.K, p.splits,
+            cudaGetErrorString(e), BLOCK_N, STAGES, A_MAJOR, B_MAJOR, MC ? 1 : 0, grid, smem_bytes, p.M, p.N, p.K, p.splits,
             dev, static_cast<void*>(stream));
   }
   return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool MC = false>
 int dispatch_major(int a_major, int b_major, const Maps& m, const GemmParams& p, int max_ctas,
                    cudaStream_t s) {
-  if (a_major == 0 && b_major == 0) return launch<BLOCK_N, STAGES, 0, 0>(m, p, max_ctas, s);
-  if (a_major == 0 && b_major == 1) return launch<BLOCK_N, STAGES, 0, 1>(m, p, max_ctas, s);
-  if (a_major == 1 && b_major == 0) return launch<BLOCK_N, STAGES, 1, 0>(m, p, max_ctas, s);
-  return launch<BLOCK_N, STAGES, 1, 1>(m, p, max_ctas, s);
+  if (a_major == 0 && b_major == 0) return launch<BLOCK_N, STAGES, 0, 0, MC>(m, p, max_ctas, s);
+  if (a_major == 0 && b_major == 1) return launch<BLOCK_N, STAGES, 0, 1, MC>(m, p, max_ctas, s);
+  if (a_major == 1 && b_major == 0) return launch<BLOCK_N, STAGES, 1, 0, MC>(m, p, max_ctas, s);
+  return launch<BLOCK_N, STAGES, 1, 1, MC>(m, p, max_ctas, s);
 }
 
 int num_sms() {
@@ -631,7 +688,13 @@ extern "C" int mg_gemm_bf16(const void* A, const void* B, void* C, const void* b
   if (a_major == 0) rc = make_map_bf16(&m.a, A, K, M, lda, BLOCK_K, BLOCK_M);
   else              rc = make_map_bf16(&m.a, A, M, K, lda, 64, BLOCK_K);
   if (rc) return rc;
-  if (b_major == 0) rc = make_map_bf16(&m.b, B, K, N, ldb, BLOCK_K, block_n);
+  // cluster-multicast variant: 128x256 tiles, at least two m-blocks, enabled by MAGGY_B200_GEMM_MC (default on)
+  static const int mc_env = [] {
+    const char* v = getenv("MAGGY_B200_GEMM_MC");
+    return v == nullptr ? 1 : atoi(v);
+  }();
+  const bool use_mc = mc_env != 0 && block_n == 256 && p.num_m_blocks >= 2;
+  if (b_major == 0) rc = make_map_bf16(&m.b, B, K, N, ldb, BLOCK_K, use_mc ? block_n / 2 : block_n);
   else              rc = make_map_bf16(&m.b, B, N, K, ldb, 64, BLOCK_K);
   if (rc) return rc - 1000;
   m.c = m.a;
@@ -647,7 +710,8 @@ extern "C" int mg_gemm_bf16(const void* A, const void* B, void* C, const void* b
 
   int max_ctas = (sm_limit > 0 && sm_limit < num_sms()) ? sm_limit : num_sms();
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256)      rc = dispatch_major<256, 4>(a_major, b_major, m, p, max_ctas, s);
+  if (block_n == 256 && use_mc) rc = dispatch_major<256, 4, true>(a_major, b_major, m, p, max_ctas, s);
+  else if (block_n == 256) rc = dispatch_major<256, 4>(a_major, b_major, m, p, max_ctas, s);
   else if (block_n == 192) rc = dispatch_major<192, 4>(a_major, b_major, m, p, max_ctas, s);
   else if (block_n == 128) rc = dispatch_major<128, 6>(a_major, b_major, m, p, max_ctas, s);
   else return -4;

@@ -339,3 +339,26 @@ def test_gang_members_stop_together(monkeypatch):
                                   es_policy="median", es_interval=1, es_min=2, name="gang_es", gpus_per_trial=2, seed=2)
     res = experiment.lagom(train_gang_early_stop, cfg)
     assert res["num_trials"] == 8 and res["early_stopped"] >= 1
+
+
+def test_gang_ablation_payload_with_closures(monkeypatch):
+    """Ablation payloads carry local closures: the gang leader must be able to forward them to followers."""
+    import torch
+
+    monkeypatch.setenv("MAGGY_NUM_EXECUTORS", "2")
+
+    def base():
+        return torch.nn.Sequential(torch.nn.Linear(2, 2), torch.nn.ReLU(), torch.nn.Linear(2, 1))
+
+    study = AblationStudy("ds", 1, label_name="y", dataset_generator=lambda: None)
+    study.model.set_base_model_generator(base)
+    study.model.layers.include("1")
+
+    def train(hparams):
+        import torch.distributed as dist
+
+        model = hparams["model_function"]()
+        return float(sum(isinstance(m, torch.nn.Identity) for m in model.modules())) + 0.0 * dist.get_world_size()
+
+    res = experiment.lagom(train, AblationConfig(ablation_study=study, direction="max", name="gang_abl", gpus_per_trial=2))
+    assert res["num_trials"] == 2 and sorted(res["metric_list"]) == [0.0, 1.0]
