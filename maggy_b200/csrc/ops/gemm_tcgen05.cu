@@ -693,7 +693,10 @@ extern "C" int mg_gemm_bf16(const void* A, const void* B, void* C, const void* b
     const char* v = getenv("MAGGY_B200_GEMM_MC");
     return v == nullptr ? 1 : atoi(v);
   }();
-  const bool use_mc = mc_env != 0 && block_n == 256 && p.num_m_blocks >= 2;
+  // Measured (profiles/gemm_bench_mc.md): multicast pays when the mainloop is long enough for operand traffic
+  // to dominate (8192^3: 1327 -> 1469 TFLOP/s) and is neutral on the K = 768 shapes, which are bound by the
+  // power-capped tensor pipe + epilogue; so it is only used from K = 2048 up (mc_env = 2 forces it everywhere).
+  const bool use_mc = mc_env != 0 && block_n == 256 && p.num_m_blocks >= 2 && (p.num_k_blocks >= 32 || mc_env == 2);
   if (b_major == 0) rc = make_map_bf16(&m.b, B, K, N, ldb, BLOCK_K, use_mc ? block_n / 2 : block_n);
   else              rc = make_map_bf16(&m.b, B, N, K, ldb, 64, BLOCK_K);
   if (rc) return rc - 1000;
