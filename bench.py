@@ -34,7 +34,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch"])
     ap.add_argument("--model", default="gpt2-small")
-    ap.add_argument("--batch", type=int, default=32, help="sequences per GPU per step")
+    ap.add_argument("--batch", type=int, default=64, help="sequences per GPU per step")
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-multicast", action="store_true", help="force the peer load/store variant of the fused kernel")

@@ -92,13 +92,19 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 // MC = true: thread-block clusters of 2 CTAs that work on vertically adjacent output tiles (same n-block,
 // m-blocks 2i and 2i+1). Each CTA fetches only HALF of the shared B tile and TMA-multicasts it into both
 // CTAs' shared memory, which cuts the L2 -> smem operand traffic per CTA from 48 KB to 32 KB per k-block.
-template <int BLOCK_N, int STAGES, int A_MAJOR, int B_MAJOR, bool MC>
+// MODE 2 (PAIR): the two CTAs of a cluster form a tcgen05 CTA pair: ONE `tcgen05.mma.cta_group::2` (M = 256,
+// issued by the leader CTA) multiplies both CTAs' A tiles with a B tile whose N columns are split between the
+// two shared memories, so each SM stages and reads only half of B — the shared-memory bandwidth (TMA fill +
+// MMA operand reads) per SM drops from ~190 to ~128 B/clk, which is what caps the 1-CTA kernel near 67 %
+// tensor-pipe utilisation (profiles/gemm_ncu_v2.md).
+template <int BLOCK_N, int STAGES, int A_MAJOR, int B_MAJOR, int MODE>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                          const __grid_constant__ CUtensorMap tma_b,
                          const __grid_constant__ CUtensorMap tma_c,
                          const __grid_constant__ CUtensorMap tma_aux, const GemmParams p) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  constexpr bool MC = MODE == 1, PAIR = MODE == 2, CL = MODE != 0;
+  using L = SmemLayout<(PAIR ? BLOCK_N / 2 : BLOCK_N), STAGES>;  // PAIR: each CTA stages half of the B tile
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is only guaranteed 16B aligned by the ABI: round up to the 1024B swizzle atom
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -112,17 +118,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   uint32_t crank = 0;
-  if constexpr (MC) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  if constexpr (CL) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   // iteration domain: one work unit per CTA (MC = false) or per CTA pair (MC = true)
-  const int m_groups = MC ? (p.num_m_blocks + 1) / 2 : p.num_m_blocks;
+  const int m_groups = CL ? (p.num_m_blocks + 1) / 2 : p.num_m_blocks;
   const int num_tiles = m_groups * p.num_n_blocks;
   const int num_units = num_tiles * p.splits;
-  const int unit_begin = MC ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int unit_step = MC ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int unit_begin = CL ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int unit_step = CL ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   auto coords = [&](int tile, int& m_blk, int& n_blk) {
     int mg;
     tile_coords(tile, m_groups, p.num_n_blocks, mg, n_blk);
-    m_blk = MC ? mg * 2 + static_cast<int>(crank) : mg;
+    m_blk = CL ? mg * 2 + static_cast<int>(crank) : mg;
   };
   constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 256) ? 256 : 512;  // allocation must be a power of two
 
@@ -136,22 +142,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], MC ? 2 : 1);  // MC: the peer multicasts into this stage too
+      mbar_init(&full_bar[s], PAIR ? 2 : 1);   // PAIR: both producers arrive on the leader's barrier
+      mbar_init(&empty_bar[s], MC ? 2 : 1);    // MC: the peer multicasts into this stage too
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], PAIR ? 8 : 4);  // PAIR: the peer's epilogue warps arrive here too
     }
     fence_barrier_init();
   }
   if (warp_idx == 2) {
-    tmem_alloc(tmem_ptr_smem, kTmemCols);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_2cta(tmem_ptr_smem, kTmemCols);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_ptr_smem, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC) cluster_sync();  // peer barriers must be initialised before anything is multicast at them
+  if constexpr (CL) cluster_sync();  // peer barriers must be initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -171,8 +182,29 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
           const int k0 = kb * BLOCK_K;
+          if constexpr (PAIR) {
+            // every byte of both CTAs' loads is accounted on the LEADER's barrier (only the leader issues MMAs)
+            const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+            else mbar_arrive_cluster(lead_bar);
+            if constexpr (A_MAJOR == 0) {
+              tma_load_2d_2sm(sa, &tma_a, lead_bar, k0, m0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BLOCK_M / 64; ++c)
+                tma_load_2d_2sm(sa + c * (BLOCK_K * 128), &tma_a, lead_bar, m0 + c * 64, k0);
+            }
+            if constexpr (B_MAJOR == 0) {
+              tma_load_2d_2sm(sb, &tma_b, lead_bar, k0, n0 + static_cast<int>(crank) * (BLOCK_N / 2));
+            } else {
+#pragma unroll
+              for (int c = 0; c < BLOCK_N / 128; ++c)
+                tma_load_2d_2sm(sb + c * (BLOCK_K * 128), &tma_b, lead_bar,
+                                n0 + (static_cast<int>(crank) * (BLOCK_N / 128) + c) * 64, k0);
+            }
+          } else {
+          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
           if constexpr (A_MAJOR == 0) {
             tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);
           } else {
@@ -201,6 +233,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
               }
             }
           }
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -210,8 +243,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     }
   } else if (warp_idx == 1) {
     // ============================ MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kFmtBF16, kFmtBF16, A_MAJOR, B_MAJOR, BLOCK_M, BLOCK_N);
+    if (lane == 0 && (!PAIR || crank == 0)) {
+      constexpr uint32_t idesc =
+          make_idesc(kFmtBF16, kFmtBF16, A_MAJOR, B_MAJOR, PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -239,11 +273,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
             const uint64_t db = (B_MAJOR == 0)
                                     ? make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024)
                                     : make_smem_desc_sw128(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024);
-            umma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (PAIR) umma_f16_ss_2cta(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if constexpr (MC) umma_commit_mc(&empty_bar[stage], 0x3);  // release the slot in BOTH CTAs
+          if constexpr (PAIR) umma_commit_2cta_mc(&empty_bar[stage], 0x3);
+          else if constexpr (MC) umma_commit_mc(&empty_bar[stage], 0x3);  // release the slot in BOTH CTAs
           else umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
+          if (kb == kb1 - 1) {
+            if constexpr (PAIR) umma_commit_2cta_mc(&tmem_full[as], 0x3);  // both CTAs' epilogues may start
+            else umma_commit(&tmem_full[as]);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -256,6 +295,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   } else if (warp_idx >= kEpiWarpBase) {
     // ============================ epilogue ================================
     const int q = warp_idx - kEpiWarpBase;  // == warp_idx % 4: TMEM lane quarter this warp may read
+    auto arrive_tmem_empty = [&](uint64_t* bar) {
+      if (PAIR && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));  // the leader's MMA warp waits there
+      else mbar_arrive(bar);
+    };
     uint8_t* out_stage = smem + L::kOutOffset + q * 8192;  // two 4 KB buffers for this warp
     int obuf = 0;
     int as = 0;
@@ -312,7 +355,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
             // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp now
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (lane == 0) arrive_tmem_empty(&tmem_empty[as]);
           }
           float v[64];
 #pragma unroll
@@ -449,7 +492,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (lane == 0) arrive_tmem_empty(&tmem_empty[as]);
       }
       as ^= 1;
       if (as == 0) aphase ^= 1;
@@ -459,10 +502,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC) cluster_sync();  // nobody leaves while the peer may still multicast into / arrive on this CTA
+  if constexpr (CL) cluster_sync();  // nobody leaves while the peer may still multicast into / arrive on this CTA
   if (warp_idx == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (PAIR) tmem_dealloc_2cta(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -539,10 +583,11 @@ struct Maps {
   CUtensorMap a, b, c, aux;
 };
 
-template <int BLOCK_N, int STAGES, int A_MAJOR, int B_MAJOR, bool MC>
+template <int BLOCK_N, int STAGES, int A_MAJOR, int B_MAJOR, int MODE>
 int launch(const Maps& m, const GemmParams& p, int max_ctas, cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
-  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, STAGES, A_MAJOR, B_MAJOR, MC>;
+  constexpr bool MC = MODE != 0;  // launched as 2-CTA clusters
+  using L = SmemLayout<(MODE == 2 ? BLOCK_N / 2 : BLOCK_N), STAGES>;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, STAGES, A_MAJOR, B_MAJOR, MODE>;
   constexpr int smem_bytes = L::kTotal + 1024;
   static_assert(smem_bytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
   static bool configured = false;
@@ -590,19 +635,19 @@ int launch(const Maps& m, const GemmParams& p, int max_ctas, cudaStream_t stream
     fprintf(stderr,
             "maggy_b200 gemm: launch failed: %s (BN=%d stages=%d A=%d B=%d MC=%d grid=%d smem=%d M=%d N=%d K=%d "
             "splits=%d dev=%d stream=%p)\n",
-            cudaGetErrorString(e), BLOCK_N, STAGES, A_MAJOR, B_MAJOR, MC ? 1 : 0, grid, smem_bytes, p.M, p.N, p.K, p.splits,
+            cudaGetErrorString(e), BLOCK_N, STAGES, A_MAJOR, B_MAJOR, MODE, grid, smem_bytes, p.M, p.N, p.K, p.splits,
             dev, static_cast<void*>(stream));
   }
   return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
 }
 
-template <int BLOCK_N, int STAGES, bool MC = false>
+template <int BLOCK_N, int STAGES, int MODE = 0>
 int dispatch_major(int a_major, int b_major, const Maps& m, const GemmParams& p, int max_ctas,
                    cudaStream_t s) {
-  if (a_major == 0 && b_major == 0) return launch<BLOCK_N, STAGES, 0, 0, MC>(m, p, max_ctas, s);
-  if (a_major == 0 && b_major == 1) return launch<BLOCK_N, STAGES, 0, 1, MC>(m, p, max_ctas, s);
-  if (a_major == 1 && b_major == 0) return launch<BLOCK_N, STAGES, 1, 0, MC>(m, p, max_ctas, s);
-  return launch<BLOCK_N, STAGES, 1, 1, MC>(m, p, max_ctas, s);
+  if (a_major == 0 && b_major == 0) return launch<BLOCK_N, STAGES, 0, 0, MODE>(m, p, max_ctas, s);
+  if (a_major == 0 && b_major == 1) return launch<BLOCK_N, STAGES, 0, 1, MODE>(m, p, max_ctas, s);
+  if (a_major == 1 && b_major == 0) return launch<BLOCK_N, STAGES, 1, 0, MODE>(m, p, max_ctas, s);
+  return launch<BLOCK_N, STAGES, 1, 1, MODE>(m, p, max_ctas, s);
 }
 
 int num_sms() {
@@ -697,7 +742,13 @@ extern "C" int mg_gemm_bf16(const void* A, const void* B, void* C, const void* b
   // to dominate (8192^3: 1327 -> 1469 TFLOP/s) and is neutral on the K = 768 shapes, which are bound by the
   // power-capped tensor pipe + epilogue; so it is only used from K = 2048 up (mc_env = 2 forces it everywhere).
   const bool use_mc = mc_env != 0 && block_n == 256 && p.num_m_blocks >= 2 && (p.num_k_blocks >= 32 || mc_env == 2);
-  if (b_major == 0) rc = make_map_bf16(&m.b, B, K, N, ldb, BLOCK_K, use_mc ? block_n / 2 : block_n);
+  // CTA-pair (cta_group::2) variant: MAGGY_B200_GEMM_PAIR=1 (takes precedence over the multicast variant)
+  static const int pair_env = [] {
+    const char* v = getenv("MAGGY_B200_GEMM_PAIR");
+    return v == nullptr ? 0 : atoi(v);
+  }();
+  const bool use_pair = pair_env != 0 && block_n == 256 && p.num_m_blocks >= 2;
+  if (b_major == 0) rc = make_map_bf16(&m.b, B, K, N, ldb, BLOCK_K, (use_mc || use_pair) ? block_n / 2 : block_n);
   else              rc = make_map_bf16(&m.b, B, N, K, ldb, 64, BLOCK_K);
   if (rc) return rc - 1000;
   m.c = m.a;
@@ -713,7 +764,8 @@ extern "C" int mg_gemm_bf16(const void* A, const void* B, void* C, const void* b
 
   int max_ctas = (sm_limit > 0 && sm_limit < num_sms()) ? sm_limit : num_sms();
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256 && use_mc) rc = dispatch_major<256, 4, true>(a_major, b_major, m, p, max_ctas, s);
+  if (block_n == 256 && use_pair) rc = dispatch_major<256, 6, 2>(a_major, b_major, m, p, max_ctas, s);
+  else if (block_n == 256 && use_mc) rc = dispatch_major<256, 4, 1>(a_major, b_major, m, p, max_ctas, s);
   else if (block_n == 256) rc = dispatch_major<256, 4>(a_major, b_major, m, p, max_ctas, s);
   else if (block_n == 192) rc = dispatch_major<192, 4>(a_major, b_major, m, p, max_ctas, s);
   else if (block_n == 128) rc = dispatch_major<128, 6>(a_major, b_major, m, p, max_ctas, s);

@@ -47,26 +47,33 @@ ce_fwd_bwd_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restric
   }
   mx = block_reduce(mx, true, scratch);
   const float kLog2e = 1.4426950408889634f;
+  // target logit must be read before the row buffer is overwritten with exp() values below
+  float x_tgt = 0.f;
+  if (threadIdx.x == 0 && !ignored) x_tgt = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(smem_row)[tgt]);
+  __syncthreads();
+  // exp() is evaluated ONCE per element (MUFU.EX2 runs at 16/clk/SM: two passes of 50k exps per row would
+  // cost more than the HBM traffic of this kernel); e = exp(x - max) is parked in the row buffer as bf16
   float sum = 0.f;
   for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
     uint4 u = srow[i];
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t e[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       float2 f = unpack_bf16x2(w[t]);
       int c = i * 8 + 2 * t;
-      if (c < v_real) sum += exp2f((f.x - mx) * kLog2e);
-      if (c + 1 < v_real) sum += exp2f((f.y - mx) * kLog2e);
+      float e0 = (c < v_real) ? exp2f((f.x - mx) * kLog2e) : 0.f;
+      float e1 = (c + 1 < v_real) ? exp2f((f.y - mx) * kLog2e) : 0.f;
+      sum += e0 + e1;
+      e[t] = pack_bf16x2(e0, e1);
     }
+    srow[i] = make_uint4(e[0], e[1], e[2], e[3]);
   }
   sum = block_reduce(sum, false, scratch);
   const float inv_sum = 1.0f / sum;
   if (threadIdx.x == 0) {
     float loss = 0.f;
-    if (!ignored) {
-      float xt = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(smem_row)[tgt]);
-      loss = logf(sum) + mx - xt;
-    }
+    if (!ignored) loss = logf(sum) + mx - x_tgt;
     losses[row] = loss;
   }
   const float gs = ignored ? 0.f : grad_scale;
@@ -78,8 +85,8 @@ ce_fwd_bwd_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restric
     for (int t = 0; t < 4; ++t) {
       float2 f = unpack_bf16x2(w[t]);
       int c = i * 8 + 2 * t;
-      float p0 = (c < v_real) ? exp2f((f.x - mx) * kLog2e) * inv_sum : 0.f;
-      float p1 = (c + 1 < v_real) ? exp2f((f.y - mx) * kLog2e) * inv_sum : 0.f;
+      float p0 = f.x * inv_sum;  // f = exp(x - max) from the pass above (0 in the padding columns)
+      float p1 = f.y * inv_sum;
       if (c == tgt) p0 -= 1.0f;
       if (c + 1 == tgt) p1 -= 1.0f;
       o[t] = pack_bf16x2(p0 * gs, p1 * gs);
