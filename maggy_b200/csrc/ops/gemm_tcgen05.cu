@@ -142,7 +142,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], PAIR ? 2 : 1);   // PAIR: both producers arrive on the leader's barrier
+      mbar_init(&full_bar[s], 1);              // PAIR: only the leader's is used (it expects both CTAs' bytes)
       mbar_init(&empty_bar[s], MC ? 2 : 1);    // MC: the peer multicasts into this stage too
     }
     for (int s = 0; s < 2; ++s) {
@@ -186,8 +186,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
           if constexpr (PAIR) {
             // every byte of both CTAs' loads is accounted on the LEADER's barrier (only the leader issues MMAs)
             const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            // the peer's bytes may land before this expect_tx (transiently negative tx-count is legal); they
+            // cannot land a phase early because the peer's slot is only released by the leader's MMA commit
             if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
-            else mbar_arrive_cluster(lead_bar);
             if constexpr (A_MAJOR == 0) {
               tma_load_2d_2sm(sa, &tma_a, lead_bar, k0, m0);
             } else {
@@ -742,10 +743,11 @@ extern "C" int mg_gemm_bf16(const void* A, const void* B, void* C, const void* b
   // to dominate (8192^3: 1327 -> 1469 TFLOP/s) and is neutral on the K = 768 shapes, which are bound by the
   // power-capped tensor pipe + epilogue; so it is only used from K = 2048 up (mc_env = 2 forces it everywhere).
   const bool use_mc = mc_env != 0 && block_n == 256 && p.num_m_blocks >= 2 && (p.num_k_blocks >= 32 || mc_env == 2);
-  // CTA-pair (cta_group::2) variant: MAGGY_B200_GEMM_PAIR=1 (takes precedence over the multicast variant)
+  // CTA-pair (cta_group::2) variant — the default for 256-wide tiles (MAGGY_B200_GEMM_PAIR=0 disables it);
+  // takes precedence over the multicast variant
   static const int pair_env = [] {
     const char* v = getenv("MAGGY_B200_GEMM_PAIR");
-    return v == nullptr ? 0 : atoi(v);
+    return v == nullptr ? 1 : atoi(v);
   }();
   const bool use_pair = pair_env != 0 && block_n == 256 && p.num_m_blocks >= 2;
   if (b_major == 0) rc = make_map_bf16(&m.b, B, K, N, ldb, BLOCK_K, (use_mc || use_pair) ? block_n / 2 : block_n);
