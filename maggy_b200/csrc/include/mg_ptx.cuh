@@ -178,6 +178,27 @@ MG_DEVICE void tma_store_2d(const CUtensorMap* map, const void* smem_src, int32_
 // 1-D bulk copies (no tensor map): global -> shared with mbarrier completion, shared -> global as a bulk group.
 // `bytes` must be a multiple of 16; both addresses 16-byte aligned. Works on peer-mapped global addresses,
 // which makes it the cheapest way to keep hundreds of KB in flight over NVLink from a single thread.
+// 4-D tiled loads / stores (NHWC activations: coordinates {c, w, h, n}); out-of-range coordinates — negative
+// ones included — are zero-filled on load and clipped on store, which is what gives the implicit-GEMM
+// convolution its padding for free.
+MG_DEVICE void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1,
+                           int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3)
+      : "memory");
+}
+MG_DEVICE void tma_store_4d(const CUtensorMap* map, const void* smem_src, int32_t c0, int32_t c1, int32_t c2,
+                            int32_t c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+MG_DEVICE void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 MG_DEVICE void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

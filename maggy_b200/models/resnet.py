@@ -1,24 +1,33 @@
 """ResNet-50 (He et al. 2015) for the ASHA HPO benchmark config ("ASHA HPO ResNet-50 synthetic, 8 concurrent
-trials on 8xB200, 1 GPU/trial", BASELINE.json). channels_last + bf16 autocast; convolutions go through
-cuDNN in this round (the implicit-GEMM conv on the tcgen05 mainloop, K7, is not written yet), the classifier
-head and the optimizer can use the maggy_b200 kernels.
+trials on 8xB200, 1 GPU/trial", BASELINE.json). channels_last bf16; every convolution runs on the maggy_b200
+tcgen05 kernels (``ops.conv.Conv2d``: implicit GEMM for the 3x3 stride-1 layers, the plain GEMM for 1x1, im2col +
+GEMM for the strided ones); ``conv_impl="torch"`` builds the cuDNN model used as the comparison arm of
+``bench/hpo_asha_resnet.py``. Batch-norm / pooling stay on ATen.
 """
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
 
+from ..ops.conv import Conv2d as _NativeConv2d
+
+
+def _conv(impl, cin, cout, k, stride=1, padding=0):
+    if impl == "torch":
+        return nn.Conv2d(cin, cout, k, stride=stride, padding=padding, bias=False)
+    return _NativeConv2d(cin, cout, k, stride=stride, padding=padding)
+
 
 class Bottleneck(nn.Module):
     expansion = 4
 
-    def __init__(self, inplanes, planes, stride=1, downsample=None):
+    def __init__(self, inplanes, planes, stride=1, downsample=None, conv_impl="native"):
         super().__init__()
-        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.conv1 = _conv(conv_impl, inplanes, planes, 1)
         self.bn1 = nn.BatchNorm2d(planes)
-        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
+        self.conv2 = _conv(conv_impl, planes, planes, 3, stride=stride, padding=1)
         self.bn2 = nn.BatchNorm2d(planes)
-        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.conv3 = _conv(conv_impl, planes, planes * 4, 1)
         self.bn3 = nn.BatchNorm2d(planes * 4)
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
@@ -32,10 +41,11 @@ class Bottleneck(nn.Module):
 
 
 class ResNet(nn.Module):
-    def __init__(self, layers=(3, 4, 6, 3), num_classes=1000, width=64, dropout=0.0):
+    def __init__(self, layers=(3, 4, 6, 3), num_classes=1000, width=64, dropout=0.0, conv_impl="native"):
         super().__init__()
         self.inplanes = width
-        self.conv1 = nn.Conv2d(3, width, 7, stride=2, padding=3, bias=False)
+        self.conv_impl = conv_impl
+        self.conv1 = _conv(conv_impl, 3, width, 7, stride=2, padding=3)
         self.bn1 = nn.BatchNorm2d(width)
         self.relu = nn.ReLU(inplace=True)
         self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
@@ -53,11 +63,11 @@ class ResNet(nn.Module):
     def _make_layer(self, planes, blocks, stride=1):
         down = None
         if stride != 1 or self.inplanes != planes * 4:
-            down = nn.Sequential(nn.Conv2d(self.inplanes, planes * 4, 1, stride=stride, bias=False),
+            down = nn.Sequential(_conv(self.conv_impl, self.inplanes, planes * 4, 1, stride=stride),
                                  nn.BatchNorm2d(planes * 4))
-        layers = [Bottleneck(self.inplanes, planes, stride, down)]
+        layers = [Bottleneck(self.inplanes, planes, stride, down, self.conv_impl)]
         self.inplanes = planes * 4
-        layers += [Bottleneck(self.inplanes, planes) for _ in range(1, blocks)]
+        layers += [Bottleneck(self.inplanes, planes, conv_impl=self.conv_impl) for _ in range(1, blocks)]
         return nn.Sequential(*layers)
 
     def forward(self, x):
@@ -67,10 +77,10 @@ class ResNet(nn.Module):
         return self.fc(self.drop(x))
 
 
-def resnet50(num_classes=1000, dropout=0.0) -> ResNet:
-    return ResNet((3, 4, 6, 3), num_classes, dropout=dropout)
+def resnet50(num_classes=1000, dropout=0.0, conv_impl="native") -> ResNet:
+    return ResNet((3, 4, 6, 3), num_classes, dropout=dropout, conv_impl=conv_impl)
 
 
-def resnet18ish(num_classes=10) -> ResNet:
+def resnet18ish(num_classes=10, conv_impl="native") -> ResNet:
     """A small bottleneck ResNet for CPU tests."""
-    return ResNet((1, 1, 1, 1), num_classes, width=16)
+    return ResNet((1, 1, 1, 1), num_classes, width=16, conv_impl=conv_impl)
