@@ -21,15 +21,51 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def make_train_fn(model_name, batch, steps_per_budget, image, classes):
+def make_train_fn(model_name, batch, steps_per_budget, image, classes, engine="graph"):
+    """engine="graph": native tcgen05 convolutions + flat-arena fused AdamW, the whole step replayed as one CUDA
+    graph (the maggy_b200 path). engine="eager": cuDNN convolutions + torch SGD, op-by-op (what the reference's
+    oblivious train_fn does on this hardware)."""
+
+    def train_fn_graph(hparams, reporter):
+        import torch
+
+        from maggy_b200.models.resnet import resnet50
+        from maggy_b200.parallel.trainer import build_trainer
+
+        dev = torch.device("cuda", 0)
+        torch.manual_seed(0)
+        model = resnet50(classes, dropout=hparams["dropout"]).to(dev).to(memory_format=torch.channels_last)
+
+        def loss_fn(m, x, y):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return torch.nn.functional.cross_entropy(m(x), y)
+
+        _, _, step_fn = build_trainer(model, (batch, 3, image, image), dev, target_shape=(batch,),
+                                      memory_format=torch.channels_last, loss_fn=loss_fn, lr=hparams["lr"] * 0.01,
+                                      betas=(hparams["momentum"], 0.999), weight_decay=hparams["wd"], warmup_iters=2)
+        x = torch.randn(batch, 3, image, image, device=dev).to(memory_format=torch.channels_last)
+        y = torch.randint(0, classes, (batch,), device=dev)
+        step_fn.load_batch(x, y)
+        steps = int(hparams.get("budget", 1)) * steps_per_budget
+        loss = None
+        for step in range(steps):
+            loss = step_fn()
+            if step % 2 == 1 or step == steps - 1:
+                reporter.broadcast(-loss.detach().float(), step)  # published from the GPU (K8), no .item()
+        return -float(loss)
+
     def train_fn(hparams, reporter):
         import torch
 
         from maggy_b200.models.resnet import resnet18ish, resnet50
 
         dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+        if engine == "graph" and dev.type == "cuda" and model_name == "resnet50":
+            return train_fn_graph(hparams, reporter)
         torch.manual_seed(0)
-        model = (resnet50(classes, dropout=hparams["dropout"]) if model_name == "resnet50" else resnet18ish(classes))
+        impl = "torch" if engine == "eager" else "native"
+        model = (resnet50(classes, dropout=hparams["dropout"], conv_impl=impl) if model_name == "resnet50"
+                 else resnet18ish(classes, conv_impl=impl))
         model = model.to(dev)
         if dev.type == "cuda":
             model = model.to(memory_format=torch.channels_last)
@@ -66,6 +102,8 @@ def main():
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--proxy-reference-rpc", action="store_true")
     ap.add_argument("--es", default="median", choices=["median", "none"])
+    ap.add_argument("--engine", default="graph", choices=["graph", "native-eager", "eager"],
+                    help="graph: native convs + fused AdamW + CUDA graph; eager: cuDNN + torch SGD (reference-style)")
     args = ap.parse_args()
     if args.proxy_reference_rpc:
         os.environ["MAGGY_B200_PROXY_REFERENCE_RPC"] = "1"
@@ -86,7 +124,7 @@ def main():
     cfg = HyperparameterOptConfig(num_trials=args.trials, optimizer=Asha(reduction_factor=2, resource_min=1, resource_max=4),
                                   searchspace=sp, direction="max", es_policy=args.es, es_interval=1, es_min=4,
                                   name="asha_resnet50", num_workers=workers, seed=0)
-    train_fn = make_train_fn(args.model, args.batch, args.steps_per_budget, image, classes)
+    train_fn = make_train_fn(args.model, args.batch, args.steps_per_budget, image, classes, engine=args.engine)
     from maggy_b200.experiment import experiment as exp_mod
 
     t0 = time.time()
@@ -117,7 +155,7 @@ def main():
         "report_to_stop_latency_ms_median": None if not lats else med(lats) * 1e3,
         "proxy_reference_rpc": bool(args.proxy_reference_rpc),
         "config": {"model": args.model, "batch": args.batch, "image": image, "steps_per_budget": args.steps_per_budget,
-                   "optimizer": "asha(rf=2, min=1, max=4)", "es_policy": args.es},
+                   "optimizer": "asha(rf=2, min=1, max=4)", "es_policy": args.es, "engine": args.engine},
     }
     print(json.dumps(out))
 

@@ -98,9 +98,49 @@ class FlatParams:
         return (p for _, p, _, _ in self.entries)
 
     def start_step(self):
-        """Mark every main_grad as unwritten: the first wgrad of the step overwrites (no memset)."""
+        """Mark every main_grad as unwritten: the first wgrad of the step overwrites (no memset).
+
+        Parameters whose gradient comes from torch autograd (see :meth:`adopt_autograd_grads`) accumulate in
+        place into their arena slice, so those slices are zeroed here instead."""
+        if getattr(self, "_fresh", False):
+            return  # nothing was written since the last call
         for _, p, _, _ in self.entries:
-            p._mg_written = False
+            p._mg_written = bool(getattr(p, "_mg_autograd", False))
+        for lo, hi in getattr(self, "_autograd_ranges", ()):
+            self.grads[lo:hi].zero_()
+        self._fresh = True
+
+    def adopt_autograd_grads(self):
+        """Parameters that are not touched by the maggy_b200 wgrad kernels (BatchNorm, ATen linear, ...) receive a
+        ``.grad`` from torch autograd. The first time that happens the value is moved into the arena and ``p.grad``
+        is re-pointed AT the arena slice: from then on autograd's AccumulateGrad adds in place, so the fused
+        optimizer sees every gradient in the one flat buffer without per-step copies."""
+        self._fresh = False
+        changed = False
+        for _, p, _, _ in self.entries:
+            g = p.grad
+            if g is None or g.data_ptr() == p.main_grad.data_ptr():
+                continue
+            if p._mg_written:
+                p.main_grad.add_(g.to(p.main_grad.dtype))
+            else:
+                p.main_grad.copy_(g)
+            p._mg_written = True
+            p._mg_autograd = True
+            p.grad = p.main_grad
+            changed = True
+        if changed:
+            # contiguous arena ranges (alignment padding included) that start_step() has to zero
+            ranges = []
+            for i, (_, p, o, k) in enumerate(self.entries):
+                if not getattr(p, "_mg_autograd", False):
+                    continue
+                hi = self.entries[i + 1][2] if i + 1 < len(self.entries) else _round_up(o + k, _ALIGN)
+                if ranges and ranges[-1][1] == o:
+                    ranges[-1][1] = hi
+                else:
+                    ranges.append([o, hi])
+            self._autograd_ranges = [tuple(r) for r in ranges]
 
     def zero_unwritten_grads(self):
         """Zero the gradient of parameters that received no wgrad this step (unused parameters)."""
@@ -190,6 +230,7 @@ class FusedAdamW:
         flat = self.flat
         lr = self.param_groups[0]["lr"] if lr is None else lr
         self.step_count += 1
+        flat.adopt_autograd_grads()
         flat.zero_unwritten_grads()
         gn = None
         if self.max_grad_norm > 0:

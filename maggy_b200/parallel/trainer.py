@@ -20,11 +20,14 @@ class TrainStep:
 
     def __init__(self, model: torch.nn.Module, optimizer: FusedAdamW, batch_shape, device,
                  use_cuda_graph: bool = True, warmup_iters: int = 3, input_dtype=torch.long,
-                 loss_fn: Optional[Callable] = None):
+                 loss_fn: Optional[Callable] = None, target_shape=None, memory_format=None):
         self.model, self.opt = model, optimizer
         self.device = torch.device(device)
         self.idx = torch.zeros(batch_shape, dtype=input_dtype, device=self.device)
-        self.tgt = torch.zeros(batch_shape, dtype=torch.long, device=self.device)
+        if memory_format is not None:
+            self.idx = self.idx.contiguous(memory_format=memory_format)
+        self.tgt = torch.zeros(batch_shape if target_shape is None else target_shape, dtype=torch.long,
+                               device=self.device)
         self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
         self.loss_fn = loss_fn
         self.graph = None
@@ -93,3 +96,19 @@ def build_gpt2_trainer(cfg, batch_size: int, seq_len: int, device, world_size: i
     opt = FusedAdamW(flat, lr=lr, weight_decay=weight_decay, use_multicast=use_multicast)
     step = TrainStep(model, opt, (batch_size, seq_len), device, use_cuda_graph=use_cuda_graph)
     return model, flat, opt, step
+
+
+def build_trainer(model: torch.nn.Module, batch_shape, device, *, target_shape=None, input_dtype=torch.float32,
+                  memory_format=None, loss_fn: Optional[Callable] = None, lr: float = 1e-3, betas=(0.9, 0.999),
+                  weight_decay: float = 0.0, use_cuda_graph: bool = True, warmup_iters: int = 3,
+                  world_size: int = 1, rank: int = 0, group=None):
+    """Any ``nn.Module`` -> flat bf16 arena + fused AdamW + captured step (used by the HPO trial functions).
+
+    Parameters whose gradients are produced by ATen autograd instead of the maggy_b200 wgrad kernels (BatchNorm,
+    ``nn.Linear`` ...) are adopted into the arena on the first step (:meth:`FlatParams.adopt_autograd_grads`)."""
+    model.to(device)
+    flat = FlatParams(model, device=device, world_size=world_size, rank=rank, group=group)
+    opt = FusedAdamW(flat, lr=lr, betas=betas, weight_decay=weight_decay)
+    step = TrainStep(model, opt, batch_shape, device, use_cuda_graph=use_cuda_graph, warmup_iters=warmup_iters,
+                     input_dtype=input_dtype, loss_fn=loss_fn, target_shape=target_shape, memory_format=memory_format)
+    return flat, opt, step

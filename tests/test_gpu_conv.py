@@ -119,3 +119,28 @@ def test_resnet_native_vs_torch():
     g2 = ref.layer1[0].conv2.weight.grad
     assert _rel(g1, g2) < 0.1
     assert torch.isfinite(native.conv1.weight.grad.float()).all()
+
+
+def test_resnet_trainstep_graph():
+    """Whole ResNet step (native convs, ATen BatchNorm adopted into the arena, fused AdamW) replayed as a CUDA graph."""
+    from maggy_b200.models.resnet import ResNet
+    from maggy_b200.parallel.trainer import build_trainer
+
+    torch.manual_seed(4)
+    dev = torch.device("cuda", 0)
+    model = ResNet((1, 1, 1, 1), 10, width=64).to(dev).to(memory_format=torch.channels_last)
+
+    def loss_fn(m, x, y):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return torch.nn.functional.cross_entropy(m(x), y)
+
+    flat, opt, step = build_trainer(model, (16, 3, 64, 64), dev, target_shape=(16,),
+                                    memory_format=torch.channels_last, loss_fn=loss_fn, lr=2e-3, warmup_iters=2)
+    x = torch.randn(16, 3, 64, 64, device=dev).to(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (16,), device=dev)
+    losses = [float(step(x, y)) for _ in range(30)]
+    assert all(l == l for l in losses)
+    assert losses[-1] < losses[0] * 0.7, losses
+    assert step.graph is not None and len(flat._autograd_ranges) >= 1
+    bn = model.bn1.weight
+    assert bn.grad is not None and bn.grad.data_ptr() == bn.main_grad.data_ptr()
