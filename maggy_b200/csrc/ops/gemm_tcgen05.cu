@@ -53,6 +53,9 @@ struct GemmParams {
   int kb_per_split;
   float* ws;       // [splits][M][N] fp32
   int num_m_blocks, num_n_blocks, num_k_blocks;
+  float alpha;     // fp8 variant: output scale applied to the accumulator, times the optional device scalars:
+  const float* scale_a;  // per-tensor dequantisation scale of A (device pointer or null)
+  const float* scale_b;
 };
 
 constexpr int kStageOutBytes = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
@@ -97,13 +100,18 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 // two shared memories, so each SM stages and reads only half of B — the shared-memory bandwidth (TMA fill +
 // MMA operand reads) per SM drops from ~190 to ~128 B/clk, which is what caps the 1-CTA kernel near 67 %
 // tensor-pipe utilisation (profiles/gemm_ncu_v2.md).
-template <int BLOCK_N, int STAGES, int A_MAJOR, int B_MAJOR, int MODE>
+// FP8 = true: both operands are e4m3 bytes (K-major only), `tcgen05.mma.kind::f8f6f4` with K = 32 per instruction;
+// a k-block is still one 128-byte swizzle row (128 elements), so the smem layout, descriptors and pipeline are
+// byte-for-byte those of the bf16 kernel and the tensor pipe does twice the FLOPs per staged byte.
+template <int BLOCK_N, int STAGES, int A_MAJOR, int B_MAJOR, int MODE, bool FP8 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                          const __grid_constant__ CUtensorMap tma_b,
                          const __grid_constant__ CUtensorMap tma_c,
                          const __grid_constant__ CUtensorMap tma_aux, const GemmParams p) {
   constexpr bool MC = MODE == 1, PAIR = MODE == 2, CL = MODE != 0;
+  constexpr int KB_ELEMS = FP8 ? 128 : BLOCK_K;  // elements per k-block (always 128 bytes)
+  static_assert(!FP8 || (A_MAJOR == 0 && B_MAJOR == 0), "fp8 operands are K-major");
   using L = SmemLayout<(PAIR ? BLOCK_N / 2 : BLOCK_N), STAGES>;  // PAIR: each CTA stages half of the B tile
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is only guaranteed 16B aligned by the ABI: round up to the 1024B swizzle atom
@@ -182,7 +190,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
-          const int k0 = kb * BLOCK_K;
+          const int k0 = kb * KB_ELEMS;
           if constexpr (PAIR) {
             // every byte of both CTAs' loads is accounted on the LEADER's barrier (only the leader issues MMAs)
             const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
@@ -245,8 +253,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   } else if (warp_idx == 1) {
     // ============================ MMA issuer ==============================
     if (lane == 0 && (!PAIR || crank == 0)) {
-      constexpr uint32_t idesc =
-          make_idesc(kFmtBF16, kFmtBF16, A_MAJOR, B_MAJOR, PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+      constexpr uint32_t kFmt = FP8 ? kFmtE4M3 : kFmtBF16;
+      constexpr uint32_t idesc = make_idesc(kFmt, kFmt, A_MAJOR, B_MAJOR, PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -274,8 +282,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
             const uint64_t db = (B_MAJOR == 0)
                                     ? make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024)
                                     : make_smem_desc_sw128(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024);
-            if constexpr (PAIR) umma_f16_ss_2cta(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            if constexpr (FP8 && PAIR) umma_f8_ss_2cta(tmem_d, da, db, idesc, acc);
+            else if constexpr (FP8) umma_f8_ss(tmem_d, da, db, idesc, acc);
+            else if constexpr (PAIR) umma_f16_ss_2cta(tmem_d, da, db, idesc, acc);
+            else umma_f16_ss(tmem_d, da, db, idesc, acc);
           }
           if constexpr (PAIR) umma_commit_2cta_mc(&empty_bar[stage], 0x3);
           else if constexpr (MC) umma_commit_mc(&empty_bar[stage], 0x3);  // release the slot in BOTH CTAs
@@ -364,6 +375,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
             v[i] = __uint_as_float(r0[i]);
             v[32 + i] = __uint_as_float(r1[i]);
           }
+          if constexpr (FP8) {
+            const float alpha = p.alpha * (p.scale_a ? __ldg(p.scale_a) : 1.f) * (p.scale_b ? __ldg(p.scale_b) : 1.f);
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] *= alpha;
+          }
           if (has_bias) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -423,6 +439,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if constexpr (FP8) {
+            const float alpha = p.alpha * (p.scale_a ? __ldg(p.scale_a) : 1.f) * (p.scale_b ? __ldg(p.scale_b) : 1.f);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= alpha;
+          }
           if (p.bias != nullptr &&
               (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RESIDUAL)) {
 #pragma unroll
@@ -563,6 +584,10 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+// 2-D byte (e4m3) tensor map: `inner` contiguous bytes, `outer` rows of `ld` bytes; 128B swizzle.
+int make_map_u8(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                uint32_t box_outer);
+
 // 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of `ld` elements; 128B swizzle.
 int make_map_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
                   uint32_t box_inner, uint32_t box_outer) {
@@ -578,17 +603,31 @@ int make_map_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t ou
   return r == CUDA_SUCCESS ? 0 : -200 - static_cast<int>(r);
 }
 
+int make_map_u8(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                uint32_t box_outer) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return -100;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -200 - static_cast<int>(r);
+}
+
 int g_num_sms = 0;
 
 struct Maps {
   CUtensorMap a, b, c, aux;
 };
 
-template <int BLOCK_N, int STAGES, int A_MAJOR, int B_MAJOR, int MODE>
+template <int BLOCK_N, int STAGES, int A_MAJOR, int B_MAJOR, int MODE, bool FP8 = false>
 int launch(const Maps& m, const GemmParams& p, int max_ctas, cudaStream_t stream) {
   constexpr bool MC = MODE != 0;  // launched as 2-CTA clusters
   using L = SmemLayout<(MODE == 2 ? BLOCK_N / 2 : BLOCK_N), STAGES>;
-  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, STAGES, A_MAJOR, B_MAJOR, MODE>;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, STAGES, A_MAJOR, B_MAJOR, MODE, FP8>;
   constexpr int smem_bytes = L::kTotal + 1024;
   static_assert(smem_bytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
   static bool configured = false;
@@ -727,6 +766,9 @@ extern "C" int mg_gemm_bf16(const void* A, const void* B, void* C, const void* b
   p.kb_per_split = (p.num_k_blocks + splits - 1) / splits;
   p.splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
   p.ws = ws;
+  p.alpha = 1.f;
+  p.scale_a = nullptr;
+  p.scale_b = nullptr;
   p.tma_store = (!out_f32 && !accumulate && p.splits == 1) ? 1 : 0;
 
   Maps m;
@@ -783,4 +825,51 @@ extern "C" int mg_gemm_bf16(const void* A, const void* B, void* C, const void* b
     if (e != cudaSuccess) return -500 - static_cast<int>(e);
   }
   return 0;
+}
+
+// fp8 (e4m3) GEMM: C[M,N] (bf16) = alpha * sum_k A(m,k) B(n,k) (+ bias[n]); A is [M][K] bytes (row stride lda),
+// B is [N][K] bytes (row stride ldb); K % 16 == 0, lda / ldb multiples of 16. The accumulator is multiplied by
+// alpha * (*scale_a) * (*scale_b): scale_a / scale_b are optional DEVICE scalars (the per-tensor dequantisation
+// scales written by mg_quant_e4m3), so quantise -> GEMM needs no host round trip. epi: EPI_NONE or EPI_BIAS.
+extern "C" int mg_gemm_fp8(const void* A, const void* B, void* C, const void* bias, int M, int N, int K,
+                           long long lda, long long ldb, long long ldc, float alpha, const float* scale_a,
+                           const float* scale_b, int epi, int sm_limit, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((N % 8) != 0 || (K % 16) != 0 || (lda % 16) != 0 || (ldb % 16) != 0 || (ldc % 8) != 0) return -1;
+  if (epi != EPI_NONE && epi != EPI_BIAS) return -3;
+  constexpr int block_n = 256;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.C = C; p.ldc = ldc;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.aux = nullptr;
+  p.ld_aux = 0;
+  p.epi = epi; p.out_f32 = 0; p.accumulate = 0;
+  p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_blocks = (N + block_n - 1) / block_n;
+  p.num_k_blocks = (K + 127) / 128;
+  p.kb_per_split = p.num_k_blocks;
+  p.splits = 1;
+  p.ws = nullptr;
+  p.tma_store = 1;
+  p.alpha = alpha;
+  p.scale_a = scale_a;
+  p.scale_b = scale_b;
+  static const int pair_env = [] {
+    const char* v = getenv("MAGGY_B200_GEMM_PAIR");
+    return v == nullptr ? 1 : atoi(v);
+  }();
+  const bool use_pair = pair_env != 0 && p.num_m_blocks >= 2;
+  Maps m;
+  int rc = make_map_u8(&m.a, A, K, M, lda, 128, BLOCK_M);
+  if (rc) return rc;
+  rc = make_map_u8(&m.b, B, K, N, ldb, 128, use_pair ? block_n / 2 : block_n);
+  if (rc) return rc - 1000;
+  rc = make_map_bf16(&m.c, C, N, M, ldc, 64, 32);
+  if (rc) return rc - 2000;
+  m.aux = m.c;
+  int max_ctas = (sm_limit > 0 && sm_limit < num_sms()) ? sm_limit : num_sms();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (use_pair) return launch<256, 6, 0, 0, 2, true>(m, p, max_ctas, s);
+  return launch<256, 4, 0, 0, 0, true>(m, p, max_ctas, s);
 }

@@ -26,6 +26,7 @@ class LlamaConfig:
     rope_theta: float = 500000.0
     norm_eps: float = 1e-5
     tie_embeddings: bool = True
+    fp8: bool = False  # forward qkv and gate-up projections in e4m3 on tcgen05 kind::f8f6f4 (bf16 backward)
 
     @classmethod
     def named(cls, name: str) -> "LlamaConfig":
@@ -67,7 +68,8 @@ class LlamaBlock(nn.Module):
         B, T, C = x.shape
         H, KV, hd = cfg.n_heads, cfg.n_kv_heads, C // cfg.n_heads
         h = F.rms_norm(x, self.attn_norm, cfg.norm_eps)
-        qkv = F.linear(h, self.wqkv)
+        lin = F.linear_fp8 if cfg.fp8 else F.linear
+        qkv = lin(h, self.wqkv)
         q, k, v = qkv.split([H * hd, KV * hd, KV * hd], dim=-1)
         q = apply_rope(q.view(B, T, H, hd), cos, sin)
         k = apply_rope(k.view(B, T, KV, hd), cos, sin)
@@ -76,7 +78,7 @@ class LlamaBlock(nn.Module):
             q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True, enable_gqa=True)
         x = F.linear(y.transpose(1, 2).reshape(B, T, C), self.wo, residual=x)
         h = F.rms_norm(x, self.ffn_norm, cfg.norm_eps)
-        gate, up = F.linear(h, self.w13).chunk(2, dim=-1)
+        gate, up = lin(h, self.w13).chunk(2, dim=-1)
         x = F.linear(torch.nn.functional.silu(gate) * up, self.w2, residual=x)
         return x
 

@@ -195,6 +195,41 @@ def sumsq(x_bf16, out_f32):
     return out_f32
 
 
+def quantize_fp8(x: torch.Tensor):
+    """Per-tensor e4m3 quantisation on the device: returns ``(q, scale)`` with ``q`` a ``torch.float8_e4m3fn``
+    tensor of ``x``'s shape and ``scale`` a 1-element fp32 device tensor such that ``x ~= q * scale``."""
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    q = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    ws = torch.empty(2, dtype=torch.float32, device=x.device)
+    lib = _lib.cuda()
+    rc = lib.mg_quant_e4m3(x.data_ptr(), q.data_ptr(), x.numel(), ws.data_ptr(), ws[1:].data_ptr(), _stream())
+    _lib.check(rc, "mg_quant_e4m3")
+    _count(2)
+    return q.view(torch.float8_e4m3fn), ws[1:]
+
+
+def gemm_fp8(a_q, b_q, scale_a=None, scale_b=None, *, bias=None, out=None, alpha: float = 1.0, sm_limit=0):
+    """``C[M,N] (bf16) = alpha * scale_a * scale_b * sum_k A(m,k) B(n,k) (+ bias)`` with e4m3 operands
+    (``a_q`` [M,K], ``b_q`` [N,K], both K-major) on ``tcgen05.mma.kind::f8f6f4``; the scales are device scalars."""
+    _need_cuda(a_q, b_q, bias, out)
+    assert a_q.element_size() == 1 and b_q.element_size() == 1 and a_q.dim() == 2 and b_q.dim() == 2
+    assert a_q.stride(1) == 1 and b_q.stride(1) == 1
+    M, K = a_q.shape
+    N, Kb = b_q.shape
+    assert K == Kb, f"reduction mismatch {K} vs {Kb}"
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a_q.device)
+    assert out.dtype == torch.bfloat16 and out.shape == (M, N) and out.stride(1) == 1
+    lib = _lib.cuda()
+    rc = lib.mg_gemm_fp8(a_q.data_ptr(), b_q.data_ptr(), out.data_ptr(), _ptr(bias), M, N, K, a_q.stride(0),
+                         b_q.stride(0), out.stride(0), float(alpha), _ptr(scale_a), _ptr(scale_b),
+                         EPI_BIAS if bias is not None else EPI_NONE, sm_limit, _stream())
+    _lib.check(rc, f"mg_gemm_fp8(M={M},N={N},K={K})")
+    _count(1)
+    return out
+
+
 def _write_or_return_grad(param, compute_into):
     """main_grad convention. ``compute_into(dst, accumulate)`` must fill ``dst``."""
     mg = getattr(param, "main_grad", None)
@@ -252,6 +287,42 @@ class _Linear(torch.autograd.Function):
 
 def linear(x, weight, bias=None, residual=None):
     return _Linear.apply(x, weight, bias, residual)
+
+
+class _LinearFP8(torch.autograd.Function):
+    """y = x W^T (+ b) with the forward GEMM in e4m3 (per-tensor dynamic scales, quantised on the device);
+    dgrad / wgrad stay in bf16 on the saved bf16 operands."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        xq, sx = quantize_fp8(x2)
+        wq, sw = quantize_fp8(weight if weight.is_contiguous() else weight.contiguous())
+        y = gemm_fp8(xq, wq, sx, sw, bias=bias)
+        ctx.save_for_backward(x2, weight)
+        ctx.bias, ctx.weight_ref, ctx.xshape = bias, weight, x.shape
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx = gemm(dy2, weight, b_major=MN_MAJOR).view(ctx.xshape) if ctx.needs_input_grad[0] else None
+        dw = _write_or_return_grad(
+            ctx.weight_ref,
+            lambda dst, acc: gemm(dy2, x2, a_major=MN_MAJOR, b_major=MN_MAJOR, out=dst, accumulate=acc))
+        db = None
+        if ctx.bias is not None:
+            db = _write_or_return_grad(ctx.bias, lambda dst, acc: colsum(dy2, dst, accumulate=acc))
+        return dx, dw, db
+
+
+def linear_fp8(x, weight, bias=None):
+    return _LinearFP8.apply(x, weight, bias)
 
 
 class _LayerNorm(torch.autograd.Function):

@@ -43,13 +43,40 @@ def test_only_sm100a_code_is_built():
 def test_gemm_uses_tcgen05_tmem_and_tma(sass):
     ks = _kernels(sass, "gemm_bf16_tcgen05_kernel")
     assert len(ks) >= 8                       # block_n x operand-major instantiations
+    fp8 = {k for k in ks if "Lb1EEEv" in k}    # <..., FP8 = true> instantiations
+    assert len(fp8) >= 2
     for name, text in ks.items():
-        assert "UTCHMMA" in text, name        # tcgen05.mma kind::f16
+        if name in fp8:
+            assert "UTCQMMA" in text, name    # tcgen05.mma kind::f8f6f4
+        else:
+            assert "UTCHMMA" in text, name    # tcgen05.mma kind::f16
         assert "LDTM" in text, name           # tcgen05.ld (TMEM -> registers)
         assert "UTMALDG" in text, name        # TMA loads
         assert "UTMASTG" in text, name        # TMA store epilogue
         assert "SYNCS" in text, name          # mbarrier pipeline
         assert "HMMA." not in text.replace("UTCHMMA", ""), name   # no legacy mma.sync path
+
+
+def test_pair_gemm_uses_cta_group_2(sass):
+    ks = {k: v for k, v in _kernels(sass, "gemm_bf16_tcgen05_kernel").items() if "ELi2ELb" in k}   # MODE = 2
+    assert len(ks) >= 5
+    for name, text in ks.items():
+        assert re.search(r"UTC[HQ]MMA\.2CTA", text), name       # one MMA spanning both SMs of the pair
+        assert "UTMALDG.2D.2CTA" in text, name                  # TMA loads signalling the leader's mbarrier
+        assert "UTCBAR.2CTA.MULTICAST" in text, name            # commit releases both CTAs' smem slots
+
+
+def test_conv_kernels_are_implicit_gemm_on_tcgen05(sass):
+    fprop = _kernels(sass, "conv2d_fprop_tcgen05_kernel")
+    wgrad = _kernels(sass, "conv2d_wgrad_tcgen05_kernel")
+    assert len(fprop) == 3 and len(wgrad) == 3
+    for name, text in {**fprop, **wgrad}.items():
+        assert "UTCHMMA" in text and "LDTM" in text, name
+        assert "UTMALDG.4D" in text, name                       # shifted pixel boxes straight from NHWC
+    for name, text in fprop.items():
+        assert "UTMASTG.4D" in text, name                       # output pixel box stored by TMA
+    for name, text in wgrad.items():
+        assert "REDG.E.ADD.F32x4" in text, name                 # split-pixel partial sums
 
 
 def test_allgather_gemm_mixes_peer_loads_with_tensor_core_tiles(sass):
