@@ -17,6 +17,8 @@ reference, never as a fallback).
 """
 from __future__ import annotations
 
+from typing import Optional
+
 import torch
 
 from . import _lib
@@ -228,6 +230,25 @@ def gemm_fp8(a_q, b_q, scale_a=None, scale_b=None, *, bias=None, out=None, alpha
     _lib.check(rc, f"mg_gemm_fp8(M={M},N={N},K={K})")
     _count(1)
     return out
+
+
+def attention_fwd(qkv: torch.Tensor, n_heads: int, n_kv_heads: Optional[int] = None, causal: bool = True,
+                  scale: Optional[float] = None):
+    """Fused attention forward on tcgen05 (head_dim 64). ``qkv``: [B, T, (H + 2*KVH) * 64] bf16, contiguous — the
+    fused projection output, q heads first, then k heads, then v heads. Returns ``(o [B, T, H*64], lse [B, H, T])``
+    (``lse`` in the log2 domain of the scaled scores)."""
+    _need_cuda(qkv)
+    B, T, Cw = qkv.shape
+    kvh = n_heads if n_kv_heads is None else n_kv_heads
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and Cw == (n_heads + 2 * kvh) * 64
+    o = torch.empty((B, T, n_heads * 64), dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty((B, n_heads, T), dtype=torch.float32, device=qkv.device)
+    sc = 0.125 if scale is None else float(scale)
+    rc = _lib.cuda().mg_attn_fwd(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, n_heads, kvh,
+                                 1 if causal else 0, sc, _stream())
+    _lib.check(rc, f"mg_attn_fwd(B={B},T={T},H={n_heads},KVH={kvh})")
+    _count(1)
+    return o, lse
 
 
 def _write_or_return_grad(param, compute_into):
