@@ -101,6 +101,34 @@ MG_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Parked wait: try_wait with a suspend-time hint lets the hardware put the warp to sleep until the phase flips (or
+// the hint expires) instead of re-issuing the probe loop. Kernels whose single-thread producer / MMA warps share an
+// SM sub-partition with compute warps use this so that the waiting roles stop competing for issue slots.
+MG_DEVICE void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 20000) {
+  uint64_t t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+    if (ok) return;
+    uint64_t now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > MG_MBAR_TIMEOUT_NS) {
+      printf("maggy_b200: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n",
+             static_cast<int>(blockIdx.x), static_cast<int>(threadIdx.x), smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) — loads arrive on an mbarrier with complete_tx
 // ----------------------------------------------------------------------------
@@ -364,6 +392,20 @@ MG_DEVICE void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 MG_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// registers -> TMEM, same shape as tmem_ld_32x32b_x32 (used to rescale an accumulator in place)
+MG_DEVICE void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+      "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]),
+      "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+MG_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
 //   bits [ 0,14) start address >> 4        bits [16,30) leading byte offset >> 4

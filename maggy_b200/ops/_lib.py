@@ -58,6 +58,7 @@ def cuda():
         _sig(lib.mg_gemm_fp8, [P, P, P, P, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_float, P, P, c_int, c_int, P])
         _sig(lib.mg_quant_e4m3, [P, P, c_ll, P, P, P])
         _sig(lib.mg_attn_fwd, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P])
+        _sig(lib.mg_attn_bwd, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P])
         _sig(lib.mg_set_device, [c_int])
         _sig(lib.mg_norm_fwd, [P, P, P, P, P, P, c_int, c_int, c_float, c_int, P])
         _sig(lib.mg_norm_bwd_grid, [c_int])

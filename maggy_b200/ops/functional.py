@@ -251,6 +251,48 @@ def attention_fwd(qkv: torch.Tensor, n_heads: int, n_kv_heads: Optional[int] = N
     return o, lse
 
 
+class _Attention(torch.autograd.Function):
+    """Fused attention over the packed projection output (see :func:`attention`)."""
+
+    @staticmethod
+    def forward(ctx, qkv, n_heads, n_kv_heads, causal, scale):
+        if not qkv.is_contiguous():
+            qkv = qkv.contiguous()
+        o, lse = attention_fwd(qkv, n_heads, n_kv_heads, causal, scale)
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.cfg = (n_heads, n_kv_heads, causal, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, o, lse = ctx.saved_tensors
+        H, KVH, causal, scale = ctx.cfg
+        B, T, W = qkv.shape
+        if not do.is_contiguous():
+            do = do.contiguous()
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty((B, H, T), dtype=torch.float32, device=qkv.device)
+        dq_acc = torch.empty((B, T, H * 64), dtype=torch.float32, device=qkv.device)
+        sc = 0.125 if scale is None else float(scale)
+        rc = _lib.cuda().mg_attn_bwd(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                                     delta.data_ptr(), dq_acc.data_ptr(), B, T, H, KVH, 1 if causal else 0, sc,
+                                     _stream())
+        _lib.check(rc, f"mg_attn_bwd(B={B},T={T},H={H},KVH={KVH})")
+        _count(4)
+        return dqkv, None, None, None, None
+
+
+def attention(qkv: torch.Tensor, n_heads: int, n_kv_heads: Optional[int] = None, causal: bool = True,
+              scale: Optional[float] = None) -> torch.Tensor:
+    """``softmax(scale * Q K^T [+ causal mask]) V`` on the tcgen05 attention kernels, head_dim 64.
+
+    ``qkv`` is the fused projection output ``[B, T, (H + 2*KVH) * 64]`` (q heads, then k heads, then v heads);
+    the result is ``[B, T, H*64]``, i.e. already in the layout of the output projection's input. Backward returns
+    the gradient in the same packed layout, so no split / transpose / concatenation kernels run in either direction."""
+    kvh = n_heads if n_kv_heads is None else n_kv_heads
+    return _Attention.apply(qkv, n_heads, kvh, causal, scale)
+
+
 def _write_or_return_grad(param, compute_into):
     """main_grad convention. ``compute_into(dst, accumulate)`` must fill ``dst``."""
     mg = getattr(param, "main_grad", None)

@@ -48,3 +48,24 @@ def test_attention_fwd(case):
     o_ref, lse_ref = _ref(qkv, H, KVH, causal)
     assert _rel(o, o_ref) < 1e-2
     assert (lse - lse_ref).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_attention_bwd(case):
+    from maggy_b200.ops import functional as F
+
+    B, T, H, KVH, causal = case
+    torch.manual_seed(1)
+    qkv = torch.randn(B, T, (H + 2 * KVH) * 64, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    do = torch.randn(B, T, H * 64, device="cuda").to(torch.bfloat16)
+    o = F.attention(qkv, H, KVH, causal=causal)
+    o.backward(do)
+    ref_in = qkv.detach().float().requires_grad_(True)
+    o_ref, _ = _ref(ref_in, H, KVH, causal)
+    o_ref.backward(do.float())
+    g, g_ref = qkv.grad, ref_in.grad
+    Cq, Ckv = H * 64, KVH * 64
+    assert _rel(o, o_ref) < 1e-2
+    assert _rel(g[..., :Cq], g_ref[..., :Cq]) < 2e-2, "dQ"
+    assert _rel(g[..., Cq:Cq + Ckv], g_ref[..., Cq:Cq + Ckv]) < 2e-2, "dK"
+    assert _rel(g[..., Cq + Ckv:], g_ref[..., Cq + Ckv:]) < 2e-2, "dV"
