@@ -37,6 +37,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=64, help="sequences per GPU per step")
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--attn", default="", choices=["", "sdpa", "native"],
+                    help="attention implementation of the model (default: MAGGY_B200_ATTN or sdpa)")
     ap.add_argument("--no-multicast", action="store_true", help="force the peer load/store variant of the fused kernel")
     ap.add_argument("--multicast", action="store_true", help="force the NVSwitch multimem variant (default: auto)")
     return ap.parse_args()
@@ -141,6 +143,8 @@ def main():
     from maggy_b200.ops import functional as F
 
     cfg = GPT2Config.named(args.model)
+    if args.attn:
+        cfg.attn_impl = args.attn
     B, T = args.batch, args.seq
     K, W = args.steps, max(args.warmup, 3)
 
@@ -222,7 +226,8 @@ def main():
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic random tokens, random-init weights",
         "impl": args.impl,
-        "config": {"model": args.model, "params": sum(p.numel() for p in model.parameters()) if args.impl == "ours" else None,
+        "config": {"attention": (args.attn or os.environ.get("MAGGY_B200_ATTN", "sdpa")) if args.impl == "ours" else "sdpa",
+                   "model": args.model, "params": sum(p.numel() for p in model.parameters()) if args.impl == "ours" else None,
                    "global_batch": B * world, "seq_len": T, "per_gpu_batch": B,
                    "parallelism": f"dp{world}" + ("+zero1-fused-rs-adam" if args.impl == "ours" else "+ddp+zero1"),
                    "nvls_multicast": bool(uses_mc), "cuda_graph": not args.no_graph,

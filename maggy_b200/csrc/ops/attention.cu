@@ -78,7 +78,7 @@ struct FwdSmem {
   static constexpr int kP = kV + kVStages * kKVTile;          // 2 buffers
   static constexpr int kOnes = kP + 2 * kPTile;               // [64 keys x 128 B]: column 0 is 1.0
   static constexpr int kBar = kOnes + kKVTile;
-  static constexpr int kTotal = kBar + 24 * 8 + 16;
+  static constexpr int kTotal = kBar + 26 * 8 + 16;
 };
 constexpr int kFwdSmemBytes = 113 * 1024;  // 2 x (dynamic + 1 KB reserved) must fit the SM's 228 KB
 static_assert(FwdSmem::kTotal <= kFwdSmemBytes, "forward tiles do not fit two CTAs per SM");
@@ -100,7 +100,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
   uint64_t* p_ready = bars + 17;            // 2 (4 arrivals each: one per softmax warp)
   uint64_t* p_free = bars + 19;             // 2
   uint64_t* o_full = bars + 21;             // 1
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* s_free = bars + 22;             // 2 (4 arrivals each)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -133,6 +134,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
       mbar_init(&s_full[s], 1);
       mbar_init(&p_ready[s], 4);
       mbar_init(&p_free[s], 1);
+      mbar_init(&s_free[s], 4);
     }
     mbar_init(o_full, 1);
     fence_barrier_init();
@@ -165,10 +167,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
       tma_load_3d(smem + FwdSmem::kQ, &tma_q, q_full, col_q, q0, b);
       for (int j = 0; j < num_kv; ++j) {
         const int sk = j % kKStages, sv = j % kVStages;
-        mbar_wait(&k_empty[sk], ((j / kKStages) & 1) ^ 1);
+        mbar_wait_parked(&k_empty[sk], ((j / kKStages) & 1) ^ 1);
         mbar_arrive_expect_tx(&k_full[sk], kKVTile);
         tma_load_3d(smem + FwdSmem::kK + sk * kKVTile, &tma_kv, &k_full[sk], col_k, j * kFBKV, b);
-        mbar_wait(&v_empty[sv], ((j / kVStages) & 1) ^ 1);
+        mbar_wait_parked(&v_empty[sv], ((j / kVStages) & 1) ^ 1);
         mbar_arrive_expect_tx(&v_full[sv], kKVTile);
         tma_load_3d(smem + FwdSmem::kV + sv * kKVTile, &tma_kv, &v_full[sv], col_v, j * kFBKV, b);
       }
@@ -181,7 +183,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
       const uint32_t sones = smem_u32(smem + FwdSmem::kOnes);
       auto issue_s = [&](int j) {
         const int sk = j % kKStages;
-        mbar_wait(&k_full[sk], (j / kKStages) & 1);
+        mbar_wait_parked(&k_full[sk], (j / kKStages) & 1);
         tc_fence_after();
         const uint32_t skk = smem_u32(smem + FwdSmem::kK + sk * kKVTile);
         const uint32_t tmem_s = tmem_base + (j & 1) * kFBKV;
@@ -192,14 +194,21 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
         umma_commit(&k_empty[sk]);
         umma_commit(&s_full[j & 1]);
       };
-      mbar_wait(q_full, 0);
+      mbar_wait_parked(q_full, 0);
       issue_s(0);
       if (num_kv > 1) issue_s(1);
       for (int j = 0; j < num_kv; ++j) {
         const int pb = j & 1, sv = j % kVStages;
-        mbar_wait(&p_ready[pb], (j >> 1) & 1);
+        if (j + 2 < num_kv) {
+          // S(j) sits in the softmax warps' registers: its TMEM buffer can take S(j + 2) right away, a whole
+          // tile before the probabilities of tile j are ready
+          mbar_wait_parked(&s_free[pb], (j >> 1) & 1);
+          tc_fence_after();
+          issue_s(j + 2);
+        }
+        mbar_wait_parked(&p_ready[pb], (j >> 1) & 1);
         tc_fence_after();
-        mbar_wait(&v_full[sv], (j / kVStages) & 1);
+        mbar_wait_parked(&v_full[sv], (j / kVStages) & 1);
         tc_fence_after();
         const uint32_t sp = smem_u32(smem + FwdSmem::kP + pb * kPTile);
         const uint32_t svv = smem_u32(smem + FwdSmem::kV + sv * kKVTile);
@@ -212,7 +221,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
         umma_commit(&v_empty[sv]);
         umma_commit(&p_free[pb]);
         if (j == num_kv - 1) umma_commit(o_full);
-        if (j + 2 < num_kv) issue_s(j + 2);  // its score buffer was drained before p_ready(j) was signalled
       }
     }
   } else {
@@ -232,12 +240,15 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
       const uint32_t tmem_s = tmem_base + pb * kFBKV + lane_off;
       const uint32_t sp_row = smem_u32(smem + FwdSmem::kP + pb * kPTile + row * 128);
       uint32_t ra[32], rb[32];
-      mbar_wait(&s_full[pb], (j >> 1) & 1);
+      mbar_wait_parked(&s_full[pb], (j >> 1) & 1);
       tc_fence_after();
       tmem_ld_32x32b_x32(tmem_s, ra);
       tmem_ld_32x32b_x32(tmem_s + 32, rb);
-      mbar_wait(&p_free[pb], ((j >> 1) & 1) ^ 1);  // the P V product that read this P buffer two tiles ago retired
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[pb]);
+      mbar_wait_parked(&p_free[pb], ((j >> 1) & 1) ^ 1);  // the P V product that read this P buffer two tiles ago retired
       float rs4[4] = {0.f, 0.f, 0.f, 0.f};
       // online softmax at 32-column granularity against the lazily updated reference `m`: a chunk whose max
       // exceeds m by more than 2^8 moves the reference; the accumulator in TMEM (and what this row already wrote of
@@ -273,7 +284,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
           if (j > 0) {
             // the accumulator may only be touched while no P V product is in flight: the previous tile's product
             // must have retired (its p_free commit), the next one waits for this warp's p_ready arrival
-            mbar_wait(&p_free[(j - 1) & 1], ((j - 1) >> 1) & 1);
+            mbar_wait_parked(&p_free[(j - 1) & 1], ((j - 1) >> 1) & 1);
             tc_fence_after();
             uint32_t t0[32];
 #pragma unroll 1
@@ -313,7 +324,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_
       if (lane == 0) mbar_arrive(&p_ready[pb]);
     }
     // all P V products retired: normalise and write out
-    mbar_wait(o_full, 0);
+    mbar_wait_parked(o_full, 0);
     tc_fence_after();
     float o[kD];
     {
@@ -456,7 +467,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
         const int st = it & 1;
         const int hq = g * group + it / tiles_per_head;
         const int q0 = (i_first + it % tiles_per_head) * 128;
-        mbar_wait(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_wait_parked(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&qdo_full[st], 2 * kTile);
         tma_load_3d(smem + BwdSmem::kQ + st * kTile, &tma_qkv, &qdo_full[st], hq * kD, q0, b);
         tma_load_3d(smem + BwdSmem::kdO + st * kTile, &tma_do, &qdo_full[st], hq * kD, q0, b);
@@ -471,7 +482,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
       const uint32_t sp = smem_u32(smem + BwdSmem::kP), sds = smem_u32(smem + BwdSmem::kdS);
       auto issue_sdp = [&](int it) {
         const int st = it & 1;
-        mbar_wait(&qdo_full[st], (it >> 1) & 1);
+        mbar_wait_parked(&qdo_full[st], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t sq = smem_u32(smem + BwdSmem::kQ + st * kTile);
         const uint32_t sdo = smem_u32(smem + BwdSmem::kdO + st * kTile);
@@ -485,18 +496,18 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
                       make_smem_desc_sw128(sv + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(sdp_full);
       };
-      mbar_wait(kv_full, 0);
+      mbar_wait_parked(kv_full, 0);
       issue_sdp(0);
       for (int it = 0; it < n_iter; ++it) {
         const int st = it & 1;
         if (it + 1 < n_iter) {
-          mbar_wait(sdp_free, it & 1);  // the compute warps drained S(it) / dP(it) from TMEM
+          mbar_wait_parked(sdp_free, it & 1);  // the compute warps drained S(it) / dP(it) from TMEM
           tc_fence_after();
           issue_sdp(it + 1);
         }
-        mbar_wait(pds_ready, it & 1);
+        mbar_wait_parked(pds_ready, it & 1);
         tc_fence_after();
-        mbar_wait(dq_free, (it & 1) ^ 1);  // the writers drained dQ(it - 1)
+        mbar_wait_parked(dq_free, (it & 1) ^ 1);  // the writers drained dQ(it - 1)
         tc_fence_after();
         const uint32_t sq = smem_u32(smem + BwdSmem::kQ + st * kTile);
         const uint32_t sdo = smem_u32(smem + BwdSmem::kdO + st * kTile);
@@ -538,12 +549,12 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
       const float delta_r = qi < p.T ? __ldg(p.delta + stat) : 0.f;
       const bool need_mask = (p.causal && kv0 + 128 > q0) || (kv0 + 128 > p.T);
       const int limit = p.causal ? min(qi, p.T - 1) : p.T - 1;
-      mbar_wait(sdp_full, it & 1);
+      mbar_wait_parked(sdp_full, it & 1);
       tc_fence_after();
       uint32_t rs[32], rd[32];
       tmem_ld_32x32b_x32(tmem_s + lane_off, rs);
       tmem_ld_32x32b_x32(tmem_dp + lane_off, rd);
-      mbar_wait(pds_free, (it & 1) ^ 1);  // the gradient MMAs of the previous tile no longer read P / dS
+      mbar_wait_parked(pds_free, (it & 1) ^ 1);  // the gradient MMAs of the previous tile no longer read P / dS
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         tmem_ld_wait();
@@ -578,7 +589,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
       if (lane == 0) mbar_arrive(pds_ready);
     }
     // epilogue: dV, dK (x softmax scale) -> bf16 -> staging (P / dS buffers) -> TMA stores into dqkv
-    mbar_wait(dkv_full, 0);
+    mbar_wait_parked(dkv_full, 0);
     tc_fence_after();
     const float sc = p.scale_log2 * 0.6931471805599453f;
 #pragma unroll 1
@@ -615,7 +626,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
     for (int it = 0; it < n_iter; ++it) {
       const int hq = g * group + it / tiles_per_head;
       const int qi = (i_first + it % tiles_per_head) * 128 + row;
-      mbar_wait(dq_full, it & 1);
+      mbar_wait_parked(dq_full, it & 1);
       tc_fence_after();
       uint32_t r0[32], r1[32];
       tmem_ld_32x32b_x32(tmem_dq + lane_off, r0);

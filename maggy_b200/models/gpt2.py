@@ -29,6 +29,7 @@ class GPT2Config:
     n_embd: int = 768
     padded_vocab_size: int = 0  # 0 -> round vocab up to a multiple of 128 (tile / vector friendly)
     layer_norm_eps: float = 1e-5
+    attn_impl: str = ""  # "" -> MAGGY_B200_ATTN or "sdpa"; "native" = maggy_b200 tcgen05 attention (K10)
 
     def __post_init__(self):
         if self.padded_vocab_size == 0:
@@ -46,12 +47,22 @@ class GPT2Config:
         return cls(**table[name])
 
 
+def _attn_impl(cfg) -> str:
+    """"native": the maggy_b200 tcgen05 attention kernels (K10); "sdpa": torch SDPA (cuDNN flash attention).
+    Measured on B200 (profiles/attention.md) the library kernel is still faster (forward 0.72x, backward 0.5x), so
+    "sdpa" is the default for the throughput benchmark; MAGGY_B200_ATTN=native / cfg.attn_impl select ours."""
+    import os
+
+    return getattr(cfg, "attn_impl", None) or os.environ.get("MAGGY_B200_ATTN", "sdpa")
+
+
 class Block(nn.Module):
     def __init__(self, cfg: GPT2Config):
         super().__init__()
         C = cfg.n_embd
         self.n_head = cfg.n_head
         self.eps = cfg.layer_norm_eps
+        self.attn_impl = _attn_impl(cfg)
         self.ln1_w = nn.Parameter(torch.ones(C))
         self.ln1_b = nn.Parameter(torch.zeros(C))
         self.qkv_w = nn.Parameter(torch.empty(3 * C, C))
@@ -69,11 +80,15 @@ class Block(nn.Module):
         B, T, C = x.shape
         H = self.n_head
         h = F.layer_norm(x, self.ln1_w, self.ln1_b, self.eps)
-        qkv = F.linear(h, self.qkv_w, self.qkv_b).view(B, T, 3, H, C // H)
-        q, k, v = qkv.unbind(dim=2)
-        y = torch.nn.functional.scaled_dot_product_attention(
-            q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True)
-        y = y.transpose(1, 2).reshape(B, T, C)
+        qkv = F.linear(h, self.qkv_w, self.qkv_b)
+        if self.attn_impl == "native" and C // H == 64 and qkv.is_cuda:
+            # K10: reads q/k/v straight out of the fused projection, writes [B, T, C]; no split / transpose / cat
+            y = F.attention(qkv, H, causal=True)
+        else:
+            q, k, v = qkv.view(B, T, 3, H, C // H).unbind(dim=2)
+            y = torch.nn.functional.scaled_dot_product_attention(
+                q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True)
+            y = y.transpose(1, 2).reshape(B, T, C)
         x = F.linear(y, self.proj_w, self.proj_b, residual=x)       # x + attn (residual fused)
         h = F.layer_norm(x, self.ln2_w, self.ln2_b, self.eps)
         x = F.mlp(h, self.fc_w, self.fc_b, self.fc2_w, self.fc2_b, residual=x)  # x + mlp

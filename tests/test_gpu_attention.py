@@ -69,3 +69,23 @@ def test_attention_bwd(case):
     assert _rel(g[..., :Cq], g_ref[..., :Cq]) < 2e-2, "dQ"
     assert _rel(g[..., Cq:Cq + Ckv], g_ref[..., Cq:Cq + Ckv]) < 2e-2, "dK"
     assert _rel(g[..., Cq + Ckv:], g_ref[..., Cq + Ckv:]) < 2e-2, "dV"
+
+
+def test_gpt2_native_attention_matches_sdpa():
+    from maggy_b200.models.gpt2 import GPT2, GPT2Config
+
+    torch.manual_seed(5)
+    cfg = GPT2Config(vocab_size=1000, block_size=256, n_layer=2, n_head=2, n_embd=128)
+    model = GPT2(cfg).cuda().to(torch.bfloat16)
+    idx = torch.randint(0, 1000, (4, 256), device="cuda")
+    losses, grads = [], []
+    for impl in ("sdpa", "native"):
+        for blk in model.blocks:
+            blk.attn_impl = impl
+        model.zero_grad(set_to_none=True)
+        loss = model(idx, idx)
+        loss.backward()
+        losses.append(loss.item())
+        grads.append(model.blocks[0].qkv_w.grad.float().clone())
+    assert abs(losses[0] - losses[1]) < 2e-2 * abs(losses[0])
+    assert _rel(grads[1], grads[0]) < 5e-2
