@@ -15,6 +15,8 @@ from __future__ import annotations
 
 from typing import Type
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -65,6 +67,26 @@ def get_maggy_fsdp_wrapper(module: Type[torch.nn.Module], mixed_precision: bool 
             model = module(*args, **kwargs)
             if torch.cuda.is_available():
                 model = model.cuda()
+            native = os.environ.get("MAGGY_B200_FSDP", "native") == "native"
+            if native and dist.is_initialized() and dist.get_world_size() > 1 and torch.cuda.is_available() \
+                    and dist.get_backend() == "nccl":
+                # B200 path: eligible nn.Linear layers keep only their row shard; the all-gather happens inside
+                # the forward GEMM (K3, parallel/fsdp.py). Everything else stays replicated under DDP, which is told
+                # to leave the sharded parameters alone.
+                from torch.nn.parallel import DistributedDataParallel as DDP
+
+                from ...parallel.fsdp import ShardedLinear, shard_linears
+
+                model = model.to(torch.bfloat16) if mixed_precision else model
+                n_sharded = shard_linears(model) if next(model.parameters()).dtype == torch.bfloat16 else 0
+                if n_sharded:
+                    ignore = [f"{mn}.{pn}" for mn, m in model.named_modules() if isinstance(m, ShardedLinear)
+                              for pn, _ in m.named_parameters(recurse=False)]
+                    DDP._set_params_and_buffers_to_ignore_for_model(model, ignore)
+                    has_replicated = any(p.requires_grad for n_, p in model.named_parameters() if n_ not in ignore)
+                    self.inner = DDP(model) if has_replicated else model
+                    self.n_sharded = n_sharded
+                    return
             if dist.is_initialized() and dist.get_world_size() > 1 and torch.cuda.is_available():
                 from torch.distributed.fsdp import FullyShardedDataParallel as FSDP, MixedPrecision
 

@@ -107,8 +107,25 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, long lo
   const int r0 = blockIdx.y * rows_per_slab;
   const int r1 = min(M, r0 + rows_per_slab);
   if (ok) {
-    for (int r = r0 + warp; r < r1; r += 8) {
-      uint4 u = ld_nc_v4(reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * ld) + vcol);
+    const uint4* base = reinterpret_cast<const uint4*>(x) + vcol;
+    const size_t ldv = static_cast<size_t>(ld) >> 3;
+    int r = r0 + warp;
+    // four independent 16-byte loads in flight per thread (the one-load-per-iteration version ran at about half
+    // of the copy bandwidth: profiles/train_step_breakdown.md)
+    for (; r + 24 < r1; r += 32) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = ld_nc_v4(base + static_cast<size_t>(r + 8 * k) * ldv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float2 a = unpack_bf16x2(u[k].x), b = unpack_bf16x2(u[k].y), c = unpack_bf16x2(u[k].z),
+               d = unpack_bf16x2(u[k].w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+        acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+      }
+    }
+    for (; r < r1; r += 8) {
+      uint4 u = ld_nc_v4(base + static_cast<size_t>(r) * ldv);
       float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
              d = unpack_bf16x2(u.w);
       acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
@@ -128,14 +145,25 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, long lo
   }
 }
 
-__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nslabs, int N,
-                                       __nv_bfloat16* __restrict__ out, int accumulate) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// one CTA per 32 columns: warp w sums slabs w, w + 8, ... (coalesced 128-byte rows), then the 8 warps combine
+__global__ void __launch_bounds__(256)
+colsum_finalize_kernel(const float* __restrict__ partial, int nslabs, int N,
+                       __nv_bfloat16* __restrict__ out, int accumulate) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int i = 0; i < nslabs; ++i) s += partial[static_cast<size_t>(i) * N + n];
-  if (accumulate) s += __bfloat162float(out[n]);
-  out[n] = __float2bfloat16(s);
+  if (n < N)
+    for (int i = warp; i < nslabs; i += 8) s += partial[static_cast<size_t>(i) * N + n];
+  __shared__ float red[8][33];
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    if (accumulate) t += __bfloat162float(out[n]);
+    out[n] = __float2bfloat16(t);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -282,8 +310,8 @@ extern "C" int mg_ce_fwd_bwd(void* logits, const long long* targets, float* loss
 }
 
 extern "C" int mg_colsum_slabs(int M) {
-  int s = (M + 255) / 256;
-  return s < 1 ? 1 : (s > 64 ? 64 : s);
+  int s = (M + 127) / 128;  // >= 128 rows per slab keeps the 4-deep load loop busy
+  return s < 1 ? 1 : (s > 256 ? 256 : s);
 }
 
 // partial: fp32 scratch of mg_colsum_slabs(M) * N floats
@@ -295,7 +323,7 @@ extern "C" int mg_colsum_bf16(const void* x, int M, int N, long long ld, void* o
   dim3 grid((N / 8 + 31) / 32, slabs);
   colsum_partial_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, N, ld,
                                              partial);
-  colsum_finalize_kernel<<<(N + 255) / 256, 256, 0, s>>>(partial, slabs, N,
+  colsum_finalize_kernel<<<(N + 31) / 32, 256, 0, s>>>(partial, slabs, N,
                                                          reinterpret_cast<__nv_bfloat16*>(out),
                                                          accumulate);
   return check();

@@ -27,3 +27,14 @@ def test_allgather_fused_gemm():
            "--master-addr", "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "tests", "multi", "ag_gemm_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0 and "AG_GEMM_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_sharded_linear_trains_like_the_unsharded_model():
+    import torch
+
+    n = min(torch.cuda.device_count(), 8)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29521",
+           os.path.join(ROOT, "tests", "multi", "sharded_linear_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0 and "SHARDED_LINEAR_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
