@@ -8,14 +8,16 @@ wraps it in DDP / fairscale FSDP / a DeepSpeed engine. Same contract here, diffe
   by the fused reduce-scatter + Adam + all-gather kernel over NVLink, no DDP buckets;
 * any other ``torch.nn.Module``: stock ``DistributedDataParallel`` (NCCL on GPUs, gloo on CPU) — the
   library baseline — with ``ZeroRedundancyOptimizer`` for ``zero_lvl`` 1-2 (see patching/optim.py);
-* ``zero_lvl`` 3: ``torch.distributed.fsdp.FullyShardedDataParallel`` with bf16 mixed precision when
-  requested (fairscale / DeepSpeed are not used; ``backend="deepspeed"`` maps its ZeRO stage here).
+* ``zero_lvl`` 3 (fairscale / DeepSpeed are not used; ``backend="deepspeed"`` maps its ZeRO stage here): bf16
+  modules get their eligible ``nn.Linear`` layers replaced by :class:`maggy_b200.parallel.fsdp.ShardedLinear` (row
+  shards in symmetric memory, all-gather fused into the forward GEMM — K3) with the remaining parameters replicated
+  under DDP; anything else (``MAGGY_B200_FSDP=torch``, fp32 modules, gloo) falls back to
+  ``torch.distributed.fsdp.FullyShardedDataParallel``.
 """
 from __future__ import annotations
 
-from typing import Type
-
 import os
+from typing import Type
 
 import torch
 import torch.distributed as dist
