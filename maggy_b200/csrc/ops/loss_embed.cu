@@ -32,17 +32,41 @@ ce_fwd_bwd_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restric
   const long long tgt = targets[row];
   const bool ignored = (tgt == ignore_index) || tgt < 0 || tgt >= v_real;
 
+  // The whole row (100 KB at V = 50304) is fetched with a handful of bulk async copies issued by one thread — the
+  // per-thread 16-byte loads of the first version kept too few bytes in flight (48 % of the copy roofline,
+  // profiles/bw_kernels.md) — and the gradient row leaves the same way.
+  __shared__ uint64_t row_bar;
+  const uint32_t row_bytes = static_cast<uint32_t>(nvec) * 16u;
+  constexpr uint32_t kChunk = 32768;
+  if (threadIdx.x == 0) {
+    mbar_init(&row_bar, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(&row_bar, row_bytes);
+    for (uint32_t off = 0; off < row_bytes; off += kChunk)
+      bulk_load_1d(smem_row + off, reinterpret_cast<const uint8_t*>(grow) + off, min(kChunk, row_bytes - off),
+                   &row_bar);
+  }
+  __syncthreads();  // barrier initialised before anyone polls it
+  mbar_wait(&row_bar, 0);
   float mx = -INFINITY;
+  const int full_vecs = v_real >> 3;  // vectors with no padding column: no per-element bound checks
   for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-    uint4 u = ld_nc_v4(grow + i);
-    srow[i] = u;
+    uint4 u = srow[i];
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    if (i < full_vecs) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float2 f = unpack_bf16x2(w[t]);
-      int c = i * 8 + 2 * t;
-      if (c < v_real) mx = fmaxf(mx, f.x);
-      if (c + 1 < v_real) mx = fmaxf(mx, f.y);
+      for (int t = 0; t < 4; ++t) {
+        float2 f = unpack_bf16x2(w[t]);
+        mx = fmaxf(mx, fmaxf(f.x, f.y));
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 f = unpack_bf16x2(w[t]);
+        int c = i * 8 + 2 * t;
+        if (c < v_real) mx = fmaxf(mx, f.x);
+        if (c + 1 < v_real) mx = fmaxf(mx, f.y);
+      }
     }
   }
   mx = block_reduce(mx, true, scratch);
@@ -53,22 +77,40 @@ ce_fwd_bwd_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restric
   __syncthreads();
   // exp() is evaluated ONCE per element (MUFU.EX2 runs at 16/clk/SM: two passes of 50k exps per row would
   // cost more than the HBM traffic of this kernel); e = exp(x - max) is parked in the row buffer as bf16
-  float sum = 0.f;
+  float sum = 0.f, sum_b = 0.f;
+  const float mxl = mx * kLog2e;
+  auto ex2 = [](float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+  };
   for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
     uint4 u = srow[i];
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     uint32_t e[4];
+    if (i < full_vecs) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float2 f = unpack_bf16x2(w[t]);
-      int c = i * 8 + 2 * t;
-      float e0 = (c < v_real) ? exp2f((f.x - mx) * kLog2e) : 0.f;
-      float e1 = (c + 1 < v_real) ? exp2f((f.y - mx) * kLog2e) : 0.f;
-      sum += e0 + e1;
-      e[t] = pack_bf16x2(e0, e1);
+      for (int t = 0; t < 4; ++t) {
+        float2 f = unpack_bf16x2(w[t]);
+        const float e0 = ex2(fmaf(f.x, kLog2e, -mxl)), e1 = ex2(fmaf(f.y, kLog2e, -mxl));
+        sum += e0;
+        sum_b += e1;
+        e[t] = pack_bf16x2(e0, e1);
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 f = unpack_bf16x2(w[t]);
+        int c = i * 8 + 2 * t;
+        float e0 = (c < v_real) ? ex2(fmaf(f.x, kLog2e, -mxl)) : 0.f;
+        float e1 = (c + 1 < v_real) ? ex2(fmaf(f.y, kLog2e, -mxl)) : 0.f;
+        sum += e0 + e1;
+        e[t] = pack_bf16x2(e0, e1);
+      }
     }
     srow[i] = make_uint4(e[0], e[1], e[2], e[3]);
   }
+  sum += sum_b;
   sum = block_reduce(sum, false, scratch);
   const float inv_sum = 1.0f / sum;
   if (threadIdx.x == 0) {
@@ -81,17 +123,33 @@ ce_fwd_bwd_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restric
     uint4 u = srow[i];
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     uint32_t o[4];
+    const float k = inv_sum * gs;
+    if ((tgt >> 3) != i) {  // f = exp(x - max) from the pass above (0 in the padding columns)
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float2 f = unpack_bf16x2(w[t]);
-      int c = i * 8 + 2 * t;
-      float p0 = f.x * inv_sum;  // f = exp(x - max) from the pass above (0 in the padding columns)
-      float p1 = f.y * inv_sum;
-      if (c == tgt) p0 -= 1.0f;
-      if (c + 1 == tgt) p1 -= 1.0f;
-      o[t] = pack_bf16x2(p0 * gs, p1 * gs);
+      for (int t = 0; t < 4; ++t) {
+        float2 f = unpack_bf16x2(w[t]);
+        o[t] = pack_bf16x2(f.x * k, f.y * k);
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 f = unpack_bf16x2(w[t]);
+        int c = i * 8 + 2 * t;
+        float p0 = f.x * inv_sum, p1 = f.y * inv_sum;
+        if (c == tgt) p0 -= 1.0f;
+        if (c + 1 == tgt) p1 -= 1.0f;
+        o[t] = pack_bf16x2(p0 * gs, p1 * gs);
+      }
     }
-    st_na_v4(grow + i, make_uint4(o[0], o[1], o[2], o[3]));
+    srow[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (uint32_t off = 0; off < row_bytes; off += kChunk)
+      bulk_store_1d(reinterpret_cast<uint8_t*>(grow) + off, smem_row + off, min(kChunk, row_bytes - off));
+    tma_store_commit();
+    tma_store_wait_read<0>();  // shared memory must outlive the copy engine's reads
   }
 }
 
