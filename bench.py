@@ -100,24 +100,15 @@ class ClockSampler:
 
 
 def reference_arm(args):
-    """Run the UNMODIFIED reference through its own public API, or say why it cannot run."""
-    ref_dir = os.path.join(ROOT, "baseline", "_ref")
-    why = None
-    if not os.path.isdir(os.path.join(ref_dir, "maggy")):
-        why = "baseline/_ref/maggy not installed (pip --no-index install failed or was not run)"
-    else:
-        sys.path.insert(0, ref_dir)
-        try:
-            from maggy import experiment  # noqa: F401  (imports tensorflow + pyspark unconditionally)
-            from maggy.config import TorchDistributedConfig  # noqa: F401
-        except Exception as e:  # pragma: no cover - depends on the image
-            why = f"reference import fails: {type(e).__name__}: {str(e)[:160]}"
-    if why is None:
-        why = ("reference imports but its torch-distributed driver needs a Spark cluster "
-               "(pyspark) and is broken as written (_patching_fn arity, SURVEY.md 2.8)")
-    if int(os.environ.get("RANK", "0")) == 0:  # under torchrun every rank gets here: one line only
-        print(json.dumps({"impl": "reference", "unavailable": why}))
-    return 0
+    """Run the UNMODIFIED reference through its own public API (baseline/reference_arm.py), or say why it cannot."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    try:
+        import reference_arm as ra
+    except Exception as e:  # noqa: BLE001
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": f"baseline/reference_arm.py failed to import: {e}"}))
+        return 0
+    return ra.run(args)
 
 
 def main():

@@ -20,6 +20,18 @@ from ...trial import Trial
 from .abstractablator import AbstractAblator
 
 
+def _pass_through_module():
+    """``nn.Identity`` for sub-modules that are called with extra arguments (e.g. a decoder block that also receives
+    rotary tables): returns its first positional argument and ignores the rest."""
+    import torch.nn as nn
+
+    class PassThrough(nn.Identity):
+        def forward(self, x, *args, **kwargs):
+            return x
+
+    return PassThrough()
+
+
 def remove_layers(model, layer_identifier):
     """Replace the identified sub-modules of a torch model with ``nn.Identity`` (in place).
 
@@ -44,7 +56,7 @@ def remove_layers(model, layer_identifier):
         parts = name.split(".")
         for p in parts[:-1]:
             parent = getattr(parent, p)
-        setattr(parent, parts[-1], nn.Identity())
+        setattr(parent, parts[-1], _pass_through_module())
     return model
 
 
