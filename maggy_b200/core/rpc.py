@@ -120,6 +120,10 @@ class DriverChannel:
         self._buf = (MgRecord * 256)()
         self._blob = ctypes.create_string_buffer(int(self.lib.mgr_bytes(self.h)) and payload_bytes + 4096)
         self.pump = pump
+        # Python view of the worker slots with the reference's Reservations API (core/reservations.py)
+        from .reservations import Reservations
+
+        self.reservations = Reservations(num_workers)
         if pump:
             self.lib.mgr_start_pump(self.h)
 
@@ -146,6 +150,12 @@ class DriverChannel:
                 if k > 0:
                     raw = self._blob.raw[:k]
                     msg["data"] = raw.decode("utf-8", "replace") if r.type == REC_LOG else cloudpickle.loads(raw)
+            if msg["type"] == "REG":
+                self.reservations.add({"partition_id": msg["partition_id"], "task_attempt": msg["aux"],
+                                       "host_port": f"shm:{self.name}#{msg['partition_id']}",
+                                       "pid": self.worker_pid(msg["partition_id"]), "trial_id": None})
+            elif msg["type"] == "FINAL":
+                self.reservations.assign_trial(msg["partition_id"], None)
             out.append(msg)
         return out
 
@@ -160,6 +170,7 @@ class DriverChannel:
             return False
         if rc != 0:
             raise OSError(f"mgr_assign failed: {rc}")
+        self.reservations.assign_trial(worker, trial_id)
         return True
 
     def stop_trial(self, worker: int, trial_id: str):
