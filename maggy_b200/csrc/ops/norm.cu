@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(128)
 norm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                 const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean_in,
                 const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dx,
-                float* __restrict__ partial, int rows, int C) {
+                float* __restrict__ partial, int rows, int C,
+                const __nv_bfloat16* __restrict__ res_grad) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 3;
   float dg[NVEC][8], db[NVEC][8];
@@ -93,6 +94,11 @@ norm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __res
     const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * C);
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * C);
     uint4* dxr = reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * C);
+    // gradient that reaches x through the residual stream (x also feeds "x + f(norm(x))"): added here so that
+    // autograd does not launch a separate elementwise add over the whole activation
+    const uint4* rgr = res_grad == nullptr
+                           ? nullptr
+                           : reinterpret_cast<const uint4*>(res_grad + static_cast<size_t>(row) * C);
     const float mean = RMS ? 0.f : mean_in[row];
     const float rstd = rstd_in[row];
     float xh[NVEC][8], gy[NVEC][8];
@@ -124,10 +130,16 @@ norm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __res
       int v = lane + i * 32;
       if (v < nvec) {
         uint32_t o[4];
+        uint32_t rg[4] = {0u, 0u, 0u, 0u};
+        if (rgr != nullptr) {
+          const uint4 rv = ld_nc_v4(rgr + v);
+          rg[0] = rv.x; rg[1] = rv.y; rg[2] = rv.z; rg[3] = rv.w;
+        }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          float a = rstd * (gy[i][2 * t] - s1 - xh[i][2 * t] * s2);
-          float b = rstd * (gy[i][2 * t + 1] - s1 - xh[i][2 * t + 1] * s2);
+          const float2 r2 = unpack_bf16x2(rg[t]);
+          float a = rstd * (gy[i][2 * t] - s1 - xh[i][2 * t] * s2) + r2.x;
+          float b = rstd * (gy[i][2 * t + 1] - s1 - xh[i][2 * t + 1] * s2) + r2.y;
           o[t] = pack_bf16x2(a, b);
         }
         st_na_v4(dxr + v, make_uint4(o[0], o[1], o[2], o[3]));
@@ -190,7 +202,7 @@ norm_bwd_finalize_kernel(const float* __restrict__ partial, int nparts, int C,
 template <bool RMS>
 int launch_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
                const float* rstd, void* dx, float* partial, int rows, int C, int grid,
-               cudaStream_t s) {
+               cudaStream_t s, const void* res_grad) {
   const int nvec_lane = ((C >> 3) + 31) / 32;
   size_t smem = static_cast<size_t>(8) * C * sizeof(float);
 #define MG_BWD_CASE(NV)                                                                            \
@@ -201,7 +213,8 @@ int launch_bwd(const void* dy, const void* x, const void* gamma, const float* me
     k<<<grid, 128, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy),                           \
                               reinterpret_cast<const __nv_bfloat16*>(x),                            \
                               reinterpret_cast<const __nv_bfloat16*>(gamma), mean, rstd,            \
-                              reinterpret_cast<__nv_bfloat16*>(dx), partial, rows, C);              \
+                              reinterpret_cast<__nv_bfloat16*>(dx), partial, rows, C,               \
+                              reinterpret_cast<const __nv_bfloat16*>(res_grad));                    \
   }
   if (nvec_lane <= 1) MG_BWD_CASE(1)
   else if (nvec_lane <= 2) MG_BWD_CASE(2)
@@ -256,14 +269,26 @@ extern "C" int mg_norm_bwd_grid(int rows) {
   return g < 592 ? g : 592;  // 148 SMs x 4 resident CTAs
 }
 
+extern "C" int mg_norm_bwd_res(const void* dy, const void* x, const void* gamma, const float* mean,
+                               const float* rstd, void* dx, void* dgamma, void* dbeta, float* partial,
+                               int rows, int C, int rms, int accumulate, const void* res_grad, void* stream);
+
 extern "C" int mg_norm_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
                            const float* rstd, void* dx, void* dgamma, void* dbeta, float* partial,
                            int rows, int C, int rms, int accumulate, void* stream) {
+  return mg_norm_bwd_res(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, partial, rows, C, rms, accumulate, nullptr,
+                         stream);
+}
+
+// res_grad (optional, [rows, C] bf16): added to dx — the gradient arriving through the residual connection
+extern "C" int mg_norm_bwd_res(const void* dy, const void* x, const void* gamma, const float* mean,
+                               const float* rstd, void* dx, void* dgamma, void* dbeta, float* partial,
+                               int rows, int C, int rms, int accumulate, const void* res_grad, void* stream) {
   if (C % 8 != 0 || C > 2048) return -1;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int grid = mg_norm_bwd_grid(rows);
-  int rc = rms ? launch_bwd<true>(dy, x, gamma, mean, rstd, dx, partial, rows, C, grid, s)
-               : launch_bwd<false>(dy, x, gamma, mean, rstd, dx, partial, rows, C, grid, s);
+  int rc = rms ? launch_bwd<true>(dy, x, gamma, mean, rstd, dx, partial, rows, C, grid, s, res_grad)
+               : launch_bwd<false>(dy, x, gamma, mean, rstd, dx, partial, rows, C, grid, s, res_grad);
   if (rc) return rc;
   norm_bwd_finalize_kernel<<<(2 * C + 31) / 32, 256, 0, s>>>(
       partial, grid, C, reinterpret_cast<__nv_bfloat16*>(dgamma),

@@ -63,6 +63,7 @@ class Block(nn.Module):
         self.n_head = cfg.n_head
         self.eps = cfg.layer_norm_eps
         self.attn_impl = _attn_impl(cfg)
+        self.fold_residual_grad = __import__("os").environ.get("MAGGY_B200_LN_RES", "1") != "0"
         self.ln1_w = nn.Parameter(torch.ones(C))
         self.ln1_b = nn.Parameter(torch.zeros(C))
         self.qkv_w = nn.Parameter(torch.empty(3 * C, C))
@@ -79,7 +80,10 @@ class Block(nn.Module):
     def forward(self, x):
         B, T, C = x.shape
         H = self.n_head
-        h = F.layer_norm(x, self.ln1_w, self.ln1_b, self.eps)
+        # x_res aliases x: routing the residual through the norm op folds the residual-gradient add into its backward
+        fold = self.fold_residual_grad
+        h, x_res = F.layer_norm(x, self.ln1_w, self.ln1_b, self.eps, with_residual=True) if fold else \
+            (F.layer_norm(x, self.ln1_w, self.ln1_b, self.eps), x)
         qkv = F.linear(h, self.qkv_w, self.qkv_b)
         if self.attn_impl == "native" and C // H == 64 and qkv.is_cuda:
             # K10: reads q/k/v straight out of the fused projection, writes [B, T, C]; no split / transpose / cat
@@ -89,9 +93,10 @@ class Block(nn.Module):
             y = torch.nn.functional.scaled_dot_product_attention(
                 q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True)
             y = y.transpose(1, 2).reshape(B, T, C)
-        x = F.linear(y, self.proj_w, self.proj_b, residual=x)       # x + attn (residual fused)
-        h = F.layer_norm(x, self.ln2_w, self.ln2_b, self.eps)
-        x = F.mlp(h, self.fc_w, self.fc_b, self.fc2_w, self.fc2_b, residual=x)  # x + mlp
+        x = F.linear(y, self.proj_w, self.proj_b, residual=x_res)   # x + attn (residual fused)
+        h, x_res = F.layer_norm(x, self.ln2_w, self.ln2_b, self.eps, with_residual=True) if fold else \
+            (F.layer_norm(x, self.ln2_w, self.ln2_b, self.eps), x)
+        x = F.mlp(h, self.fc_w, self.fc_b, self.fc2_w, self.fc2_b, residual=x_res)  # x + mlp
         return x
 
 

@@ -128,17 +128,24 @@ def layer_norm_fwd(x2d, weight, bias, eps=1e-5, rms=False):
     return y, mean, rstd
 
 
-def layer_norm_bwd(dy2d, x2d, weight, mean, rstd, dgamma, dbeta, rms=False, accumulate=False):
-    _need_cuda(dy2d, x2d)
+def layer_norm_bwd(dy2d, x2d, weight, mean, rstd, dgamma, dbeta, rms=False, accumulate=False, res_grad=None):
+    """``res_grad`` ([rows, C] bf16, optional) is added to the returned ``dx`` inside the kernel (the gradient that
+    reaches ``x`` through a residual connection around the normalised branch)."""
+    _need_cuda(dy2d, x2d, res_grad)
     rows, C = x2d.shape
     dy2d = dy2d.contiguous()
+    if res_grad is not None:
+        res_grad = res_grad.reshape(rows, C)
+        if not res_grad.is_contiguous():
+            res_grad = res_grad.contiguous()
     dx = torch.empty_like(x2d)
     lib = _lib.cuda()
     grid = lib.mg_norm_bwd_grid(rows)
     partial = _scratch_f32("norm_bwd", grid * 2 * C, x2d.device)
-    rc = lib.mg_norm_bwd(dy2d.data_ptr(), x2d.data_ptr(), weight.data_ptr(), _ptr(mean),
-                         rstd.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), _ptr(dbeta),
-                         partial.data_ptr(), rows, C, 1 if rms else 0, 1 if accumulate else 0, _stream())
+    rc = lib.mg_norm_bwd_res(dy2d.data_ptr(), x2d.data_ptr(), weight.data_ptr(), _ptr(mean),
+                             rstd.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), _ptr(dbeta),
+                             partial.data_ptr(), rows, C, 1 if rms else 0, 1 if accumulate else 0, _ptr(res_grad),
+                             _stream())
     _lib.check(rc, "mg_norm_bwd")
     _count(2)
     return dx
@@ -389,8 +396,12 @@ def linear_fp8(x, weight, bias=None):
 
 
 class _LayerNorm(torch.autograd.Function):
+    """``with_residual=True`` additionally returns ``x`` itself (an alias, no kernel) as the tensor to feed into the
+    residual connection around the normalised branch: both gradients then arrive in THIS backward and are summed
+    inside the norm-backward kernel instead of by a separate autograd add over the whole activation."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, rms):
+    def forward(ctx, x, weight, bias, eps, rms, with_residual=False):
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
@@ -398,11 +409,16 @@ class _LayerNorm(torch.autograd.Function):
         ctx.save_for_backward(x2, weight, mean if mean is not None else rstd, rstd)
         ctx.w_ref, ctx.b_ref, ctx.rms = weight, bias, rms
         ctx.xshape = x.shape
+        ctx.with_residual = with_residual
+        if with_residual:
+            return y.view(x.shape), x.view_as(x)
         return y.view(x.shape)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dres=None):
         x2, weight, mean, rstd = ctx.saved_tensors
+        if dy is None:  # only the residual stream carried a gradient
+            dy = torch.zeros(ctx.xshape, dtype=x2.dtype, device=x2.device)
         dy2 = dy.reshape(-1, dy.shape[-1])
         w, b = ctx.w_ref, ctx.b_ref
         use_main = getattr(w, "main_grad", None) is not None
@@ -418,18 +434,21 @@ class _LayerNorm(torch.autograd.Function):
             dgamma = torch.empty_like(w)
             dbeta = torch.empty_like(b) if b is not None else None
         dx = layer_norm_bwd(dy2, x2, weight, None if ctx.rms else mean, rstd, dgamma, dbeta,
-                            rms=ctx.rms, accumulate=acc)
+                            rms=ctx.rms, accumulate=acc, res_grad=dres if ctx.with_residual else None)
         if use_main:
-            return dx.view(ctx.xshape), None, None, None, None
-        return dx.view(ctx.xshape), dgamma, dbeta, None, None
+            return dx.view(ctx.xshape), None, None, None, None, None
+        return dx.view(ctx.xshape), dgamma, dbeta, None, None, None
 
 
-def layer_norm(x, weight, bias, eps=1e-5):
-    return _LayerNorm.apply(x, weight, bias, eps, False)
+def layer_norm(x, weight, bias, eps=1e-5, with_residual=False):
+    """``with_residual=True`` returns ``(norm(x), x_res)``: use ``x_res`` as the residual input of the branch
+    (``linear(..., residual=x_res)`` / ``mlp(..., residual=x_res)``) to fold the residual-gradient add into the norm
+    backward kernel."""
+    return _LayerNorm.apply(x, weight, bias, eps, False, with_residual)
 
 
-def rms_norm(x, weight, eps=1e-6):
-    return _LayerNorm.apply(x, weight, None, eps, True)
+def rms_norm(x, weight, eps=1e-6, with_residual=False):
+    return _LayerNorm.apply(x, weight, None, eps, True, with_residual)
 
 
 class _MLP(torch.autograd.Function):

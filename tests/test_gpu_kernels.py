@@ -327,3 +327,29 @@ def test_llama_and_bert_train_steps():
             losses.append(loss.item())
         assert abs(losses[0] - math.log(vocab)) < 0.7, losses
         assert losses[-1] < losses[0] - 0.05, losses
+
+
+@pytest.mark.gpu
+def test_layer_norm_residual_gradient_is_folded_into_backward():
+    """layer_norm(..., with_residual=True): x + f(norm(x)) gets the same gradients as the unfused graph, and no
+    separate add kernel is needed for the residual stream."""
+    from maggy_b200.ops import functional as F
+
+    torch.manual_seed(0)
+    C = 768
+    x = torch.randn(4, 256, C, device="cuda").to(torch.bfloat16)
+    w = (1 + 0.1 * torch.randn(C, device="cuda")).to(torch.bfloat16).requires_grad_(True)
+    b = (0.1 * torch.randn(C, device="cuda")).to(torch.bfloat16).requires_grad_(True)
+    lw = (torch.randn(C, C, device="cuda") / 28).to(torch.bfloat16).requires_grad_(True)
+    g = torch.randn(4, 256, C, device="cuda").to(torch.bfloat16)
+    x1 = x.clone().requires_grad_(True)
+    h, xr = F.layer_norm(x1, w, b, 1e-5, with_residual=True)
+    y1 = F.linear(h, lw, None, residual=xr)
+    y1.backward(g)
+    gx1, gw1 = x1.grad.clone(), w.grad.clone()
+    w.grad = b.grad = lw.grad = None
+    x2 = x.clone().float().requires_grad_(True)
+    ref = x2 + torch.nn.functional.linear(torch.nn.functional.layer_norm(x2, (C,), w.float(), b.float(), 1e-5), lw.float())
+    ref.backward(g.float())
+    assert ((y1.float() - ref).norm() / ref.norm()).item() < 1e-2
+    assert ((gx1.float() - x2.grad).norm() / x2.grad.norm()).item() < 1.5e-2
