@@ -153,6 +153,77 @@ ce_fwd_bwd_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restric
   }
 }
 
+// Vocabularies whose row does not fit in shared memory (e.g. Llama-3: 128256 columns = 250 KB): three streaming passes
+// over the row (max, sum of exponentials, gradient); the re-reads hit L2 (a row is a few hundred KB).
+__global__ void __launch_bounds__(1024)
+ce_fwd_bwd_stream_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restrict__ targets,
+                         float* __restrict__ losses, int v_real, int v_pad, long long ld, float grad_scale,
+                         int ignore_index) {
+  __shared__ float scratch[32];
+  const int row = blockIdx.x;
+  uint4* grow = reinterpret_cast<uint4*>(logits + static_cast<size_t>(row) * ld);
+  const int nvec = v_pad >> 3;
+  const long long tgt = targets[row];
+  const bool ignored = (tgt == ignore_index) || tgt < 0 || tgt >= v_real;
+  const float kLog2e = 1.4426950408889634f;
+  auto ex2 = [](float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+  };
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const uint4 u = grow[i];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = unpack_bf16x2(w[t]);
+      const int c = i * 8 + 2 * t;
+      if (c < v_real) mx = fmaxf(mx, f.x);
+      if (c + 1 < v_real) mx = fmaxf(mx, f.y);
+    }
+  }
+  mx = block_reduce(mx, true, scratch);
+  const float mxl = mx * kLog2e;
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const uint4 u = grow[i];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = unpack_bf16x2(w[t]);
+      const int c = i * 8 + 2 * t;
+      if (c < v_real) sum += ex2(fmaf(f.x, kLog2e, -mxl));
+      if (c + 1 < v_real) sum += ex2(fmaf(f.y, kLog2e, -mxl));
+    }
+  }
+  sum = block_reduce(sum, false, scratch);
+  const float inv_sum = 1.0f / sum;
+  if (threadIdx.x == 0) {
+    float loss = 0.f;
+    if (!ignored) loss = logf(sum) + mx - __bfloat162float(logits[static_cast<size_t>(row) * ld + tgt]);
+    losses[row] = loss;
+  }
+  __syncthreads();  // the target logit is read before any thread overwrites the row
+  const float gs = ignored ? 0.f : grad_scale;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const uint4 u = grow[i];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = unpack_bf16x2(w[t]);
+      const int c = i * 8 + 2 * t;
+      float p0 = (c < v_real) ? ex2(fmaf(f.x, kLog2e, -mxl)) * inv_sum : 0.f;
+      float p1 = (c + 1 < v_real) ? ex2(fmaf(f.y, kLog2e, -mxl)) * inv_sum : 0.f;
+      if (c == tgt) p0 -= 1.0f;
+      if (c + 1 == tgt) p1 -= 1.0f;
+      o[t] = pack_bf16x2(p0 * gs, p1 * gs);
+    }
+    st_na_v4(grow + i, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
 // partial[blockIdx.y][n] = sum over this slab's rows of x[row][n]
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, long long ld,
@@ -349,7 +420,12 @@ extern "C" int mg_ce_fwd_bwd(void* logits, const long long* targets, float* loss
                              int ignore_index, void* stream) {
   if (v_pad % 8 != 0 || ld % 8 != 0) return -1;
   size_t smem = static_cast<size_t>(v_pad) * 2;
-  if (smem > 200 * 1024) return -2;
+  if (smem > 110 * 1024) {
+    // the row would not leave room for two CTAs per SM (or does not fit at all): streaming variant
+    ce_fwd_bwd_stream_kernel<<<rows, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<__nv_bfloat16*>(logits), targets, losses, v_real, v_pad, ld, grad_scale, ignore_index);
+    return check();
+  }
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(ce_fwd_bwd_kernel,

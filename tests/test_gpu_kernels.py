@@ -176,6 +176,23 @@ def test_cross_entropy(F):
     assert g[:, v_real:].abs().max().item() == 0.0
 
 
+def test_cross_entropy_large_vocab_streaming_path(F):
+    """Rows that do not fit in shared memory (Llama-3 vocabulary) take the streaming kernel."""
+    torch.manual_seed(55)
+    rows, v_real, v_pad = 64, 128256, 128256
+    logits = torch.randn(rows, v_pad, device=DEV, dtype=torch.bfloat16) * 2
+    tgt = torch.randint(0, v_real, (rows,), device=DEV)
+    tgt[3] = -100
+    lr = logits.float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lr, tgt, ignore_index=-100, reduction="sum") / rows
+    ref.backward()
+    work = logits.clone().requires_grad_(True)
+    loss = F.cross_entropy(work, tgt, v_real=v_real)
+    assert abs(loss.item() - ref.item()) < 2e-2 * abs(ref.item())
+    loss.backward()
+    assert _rel_err(work.grad, lr.grad) < 1e-2
+
+
 def test_embedding(F):
     torch.manual_seed(6)
     V, T, C, B = 500, 64, 128, 4
