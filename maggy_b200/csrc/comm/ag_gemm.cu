@@ -5,8 +5,9 @@
 // The reference reaches this through fairscale FSDP: an NCCL all-gather of the flat parameter, THEN the
 // cuBLAS GEMM (maggy/core/patching/modules.py:75-95). Here one persistent kernel does both:
 //   * `n_copy` CTAs are *gather* CTAs: they pull the remote weight shards straight out of the owners' HBM
-//     over NVLink (16-byte peer loads, 8 in flight per thread) into a local gathered buffer, one 256-row
-//     block at a time, nearest shard first, and publish `ready[n_blk]` with a release store;
+//     over NVLink with 1-D bulk async copies (`cp.async.bulk`: peer HBM -> a 6 x 32 KB shared-memory ring -> local
+//     gathered buffer; one thread keeps ~190 KB in flight per gather CTA), one 256-row block at a time, nearest
+//     shard first, and publish `ready[n_blk]` with a release store;
 //   * the other CTAs are the usual TMA-producer / tcgen05-MMA / epilogue pipeline. Output tiles are
 //     visited local-shard-first, so the tensor cores start immediately on weights that are already here
 //     and by the time they need a remote block its copy has landed (the producer warp acquires
