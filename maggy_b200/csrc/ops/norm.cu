@@ -7,6 +7,8 @@
 // Stands in for the cuDNN/ATen norm kernels the reference reaches through train_fn.
 #include "../include/mg_ptx.cuh"
 
+#include <cstdlib>
+
 namespace {
 using namespace mg;
 
@@ -170,6 +172,128 @@ norm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __res
   }
 }
 
+// Variants 2 / 3 (MAGGY_B200_NORM_BWD=2: registers uncapped, 3 CTAs/SM; =3: capped at 128 registers, 4 CTAs/SM): the row is kept as the raw bf16 vectors it was loaded as (half the registers of
+// the fp32 copies above) and the NEXT row's loads are issued before the current row is reduced and written, so every
+// warp always has one row of loads in flight. The first variant spent two thirds of each row in the shuffle
+// reductions / second pass with nothing outstanding (45 % of the copy roofline, profiles/bw_kernels_v1.log).
+template <bool RMS, int NVEC, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+norm_bwd_kernel_v2(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                   const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean_in,
+                   const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dx,
+                   float* __restrict__ partial, int rows, int C,
+                   const __nv_bfloat16* __restrict__ res_grad) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  float dg[NVEC][8], db[NVEC][8];
+  uint4 gv[NVEC];
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) dg[i][t] = db[i][t] = 0.f;
+    const int v = lane + i * 32;
+    gv[i] = v < nvec ? __ldg(reinterpret_cast<const uint4*>(gamma) + v) : make_uint4(0, 0, 0, 0);
+  }
+  const float inv_c = 1.0f / static_cast<float>(C);
+  const int stride = gridDim.x * 4;
+  int row = blockIdx.x * 4 + warp;
+  uint4 xc[NVEC], dc[NVEC], xn[NVEC], dn[NVEC];
+  auto load_row = [&](int r, uint4 (&xv)[NVEC], uint4 (&dv)[NVEC]) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * C);
+    const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r) * C);
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        xv[i] = ld_nc_v4(xr + v);
+        dv[i] = ld_nc_v4(dyr + v);
+      } else {
+        xv[i] = dv[i] = make_uint4(0, 0, 0, 0);
+      }
+    }
+  };
+  if (row < rows) load_row(row, xc, dc);
+  for (; row < rows; row += stride) {
+    const int next = row + stride;
+    if (next < rows) load_row(next, xn, dn);  // in flight while this row is reduced and written
+    const float mean = RMS ? 0.f : mean_in[row];
+    const float rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const uint32_t xi[4] = {xc[i].x, xc[i].y, xc[i].z, xc[i].w}, di[4] = {dc[i].x, dc[i].y, dc[i].z, dc[i].w},
+                     gi[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 xf = unpack_bf16x2(xi[t]), df = unpack_bf16x2(di[t]), gf = unpack_bf16x2(gi[t]);
+        const float h0 = (xf.x - mean) * rstd, h1 = (xf.y - mean) * rstd;
+        const float g0 = gf.x * df.x, g1 = gf.y * df.y;
+        dg[i][2 * t] += df.x * h0; dg[i][2 * t + 1] += df.y * h1;
+        db[i][2 * t] += df.x; db[i][2 * t + 1] += df.y;
+        s1 += g0 + g1;
+        s2 += g0 * h0 + g1 * h1;
+      }
+    }
+    // padding lanes (v >= nvec) hold zeros in x: their h = -mean * rstd is harmless because dy = gamma = 0 there
+    s1 = RMS ? 0.f : warp_sum(s1) * inv_c;
+    s2 = warp_sum(s2) * inv_c;
+    uint4* dxr = reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * C);
+    const uint4* rgr = res_grad == nullptr
+                           ? nullptr
+                           : reinterpret_cast<const uint4*>(res_grad + static_cast<size_t>(row) * C);
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        const uint32_t xi[4] = {xc[i].x, xc[i].y, xc[i].z, xc[i].w}, di[4] = {dc[i].x, dc[i].y, dc[i].z, dc[i].w},
+                       gi[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+        uint32_t rg[4] = {0u, 0u, 0u, 0u};
+        if (rgr != nullptr) {
+          const uint4 rv = ld_nc_v4(rgr + v);
+          rg[0] = rv.x; rg[1] = rv.y; rg[2] = rv.z; rg[3] = rv.w;
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 xf = unpack_bf16x2(xi[t]), df = unpack_bf16x2(di[t]), gf = unpack_bf16x2(gi[t]),
+                       r2 = unpack_bf16x2(rg[t]);
+          const float h0 = (xf.x - mean) * rstd, h1 = (xf.y - mean) * rstd;
+          const float a = rstd * (gf.x * df.x - s1 - h0 * s2) + r2.x;
+          const float b = rstd * (gf.y * df.y - s1 - h1 * s2) + r2.y;
+          o[t] = pack_bf16x2(a, b);
+        }
+        st_na_v4(dxr + v, make_uint4(o[0], o[1], o[2], o[3]));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      xc[i] = xn[i];
+      dc[i] = dn[i];
+    }
+  }
+
+  extern __shared__ float red[];  // [4][2][C]
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    int v = lane + i * 32;
+    if (v < nvec) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        red[(warp * 2 + 0) * C + v * 8 + t] = dg[i][t];
+        red[(warp * 2 + 1) * C + v * 8 + t] = db[i][t];
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    int which = c / C, col = c - which * C;
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) acc += red[(w * 2 + which) * C + col];
+    partial[(static_cast<size_t>(blockIdx.x) * 2 + which) * C + col] = acc;
+  }
+}
+
 // one CTA per 32 columns: 8 warps stride over the partial rows, fold through shared memory
 __global__ void __launch_bounds__(256)
 norm_bwd_finalize_kernel(const float* __restrict__ partial, int nparts, int C,
@@ -205,9 +329,15 @@ int launch_bwd(const void* dy, const void* x, const void* gamma, const float* me
                cudaStream_t s, const void* res_grad) {
   const int nvec_lane = ((C >> 3) + 31) / 32;
   size_t smem = static_cast<size_t>(8) * C * sizeof(float);
+  static const int variant = [] {
+    const char* v = getenv("MAGGY_B200_NORM_BWD");
+    return v == nullptr ? 1 : atoi(v);
+  }();
 #define MG_BWD_CASE(NV)                                                                            \
   {                                                                                                \
-    auto k = norm_bwd_kernel<RMS, NV>;                                                             \
+    auto k = (variant == 2 && NV <= 4)   ? norm_bwd_kernel_v2<RMS, (NV <= 4 ? NV : 1), 1>          \
+             : (variant == 3 && NV <= 4) ? norm_bwd_kernel_v2<RMS, (NV <= 4 ? NV : 1), 4>          \
+                                         : norm_bwd_kernel<RMS, NV>;                               \
     if (smem > 48 * 1024)                                                                          \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
     k<<<grid, 128, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy),                           \
