@@ -725,15 +725,33 @@ int pick_block_n(int M, int N) {
 // needs it to size the fp32 workspace (splits * M * N floats). 1 means no split-K.
 extern "C" int mg_gemm_auto_splits(int M, int N, int K, int block_n) {
   if (block_n == 0) block_n = pick_block_n(M, N);
-  long long tiles = static_cast<long long>((M + BLOCK_M - 1) / BLOCK_M) * ((N + block_n - 1) / block_n);
+  const long long m_blocks = (M + BLOCK_M - 1) / BLOCK_M, n_blocks = (N + block_n - 1) / block_n;
+  long long tiles = m_blocks * n_blocks;
   int kb = (K + BLOCK_K - 1) / BLOCK_K;
   int sms = num_sms() > 0 ? num_sms() : 148;
   if (tiles * 2 > sms || kb < 32) return 1;
-  int s = static_cast<int>(sms / tiles);
-  int max_by_k = kb / 16;  // keep >= 16 k-blocks (1024 of K) per split
-  if (s > max_by_k) s = max_by_k;
-  if (s > 16) s = 16;
-  return s < 1 ? 1 : s;
+  // Work units are scheduled on CTA pairs for 256-wide tiles (one unit = two vertically adjacent tiles), on single
+  // CTAs otherwise. Pick the split count that fills whole waves best: e.g. the qkv weight gradient (18 x 3 tiles)
+  // gets 5 splits = 135 pair units = 1.82 waves (91 % busy) instead of 2 splits = 54 units (73 %). Each extra split
+  // costs one more fp32 partial of the output, hence the mild penalty; >= 16 k-blocks (1024 of K) per split.
+  const bool pairs = block_n == 256 && m_blocks >= 2;
+  const long long units1 = pairs ? ((m_blocks + 1) / 2) * n_blocks : tiles;
+  const long long slots = pairs ? sms / 2 : sms;
+  int max_s = kb / 16;
+  if (max_s > 16) max_s = 16;
+  int best = 1;
+  double best_score = 0.0;
+  for (int sp = 1; sp <= max_s; ++sp) {
+    const long long units = units1 * sp;
+    const long long waves = (units + slots - 1) / slots;
+    // time ~ waves * (K / sp): maximise sp / waves
+    const double score = static_cast<double>(sp) / static_cast<double>(waves) - 0.02 * sp;
+    if (score > best_score + 1e-9) {
+      best_score = score;
+      best = sp;
+    }
+  }
+  return best;
 }
 
 // C[M,N] = epi( sum_k A(m,k) B(n,k) ).
