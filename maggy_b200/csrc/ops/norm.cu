@@ -172,7 +172,8 @@ norm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __res
   }
 }
 
-// Variants 2 / 3 (MAGGY_B200_NORM_BWD=2: registers uncapped, 3 CTAs/SM; =3: capped at 128 registers, 4 CTAs/SM): the row is kept as the raw bf16 vectors it was loaded as (half the registers of
+// Variants 2 / 3 (MAGGY_B200_NORM_BWD=2, the default: registers uncapped, 3 CTAs/SM; =3: capped at 128 registers,
+// 4 CTAs/SM, slower because of spills; =1: the first kernel above): the row is kept as the raw bf16 vectors it was loaded as (half the registers of
 // the fp32 copies above) and the NEXT row's loads are issued before the current row is reduced and written, so every
 // warp always has one row of loads in flight. The first variant spent two thirds of each row in the shuffle
 // reductions / second pass with nothing outstanding (45 % of the copy roofline, profiles/bw_kernels_v1.log).
@@ -331,7 +332,7 @@ int launch_bwd(const void* dy, const void* x, const void* gamma, const float* me
   size_t smem = static_cast<size_t>(8) * C * sizeof(float);
   static const int variant = [] {
     const char* v = getenv("MAGGY_B200_NORM_BWD");
-    return v == nullptr ? 1 : atoi(v);
+    return v == nullptr ? 2 : atoi(v);  // measured: 1 = 0.101 ms, 2 = 0.089 ms, 3 = 0.108 ms on [65536 x 768]
   }();
 #define MG_BWD_CASE(NV)                                                                            \
   {                                                                                                \
