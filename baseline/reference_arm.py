@@ -211,7 +211,10 @@ def run(args) -> int:
     # the reference writes its experiment log under the working directory: one scratch directory per rank
     os.chdir(tempfile.mkdtemp(prefix=f"maggy_ref_rank{rank}_"))
     try:
-        ref_experiment.lagom(train_fn, BaseConfig(name="bench_reference"))
+        import contextlib
+
+        with contextlib.redirect_stdout(sys.stderr):  # the reference prints its own progress lines: keep stdout = JSON
+            ref_experiment.lagom(train_fn, BaseConfig(name="bench_reference"))
     except Exception as e:  # noqa: BLE001
         return unavailable(f"reference lagom() raised {type(e).__name__}: {str(e)[:200]}")
     if not holder or not math.isfinite(holder.get("ms", float("nan"))):
