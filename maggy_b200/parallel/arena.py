@@ -102,20 +102,16 @@ class FlatParams:
 
         Parameters whose gradient comes from torch autograd (see :meth:`adopt_autograd_grads`) accumulate in
         place into their arena slice, so those slices are zeroed here instead."""
-        if getattr(self, "_fresh", False):
-            return  # nothing was written since the last call
         for _, p, _, _ in self.entries:
             p._mg_written = bool(getattr(p, "_mg_autograd", False))
         for lo, hi in getattr(self, "_autograd_ranges", ()):
             self.grads[lo:hi].zero_()
-        self._fresh = True
 
     def adopt_autograd_grads(self):
         """Parameters that are not touched by the maggy_b200 wgrad kernels (BatchNorm, ATen linear, ...) receive a
         ``.grad`` from torch autograd. The first time that happens the value is moved into the arena and ``p.grad``
         is re-pointed AT the arena slice: from then on autograd's AccumulateGrad adds in place, so the fused
         optimizer sees every gradient in the one flat buffer without per-step copies."""
-        self._fresh = False
         changed = False
         for _, p, _, _ in self.entries:
             g = p.grad

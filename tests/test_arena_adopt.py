@@ -19,7 +19,7 @@ def test_adopt_autograd_grads_accumulate_in_place():
     assert g1.float().abs().sum() > 0
     flat.start_step()
     assert flat.grads.float().abs().sum() == 0
-    flat.start_step()  # idempotent while nothing has been written
+    flat.start_step()  # idempotent
     m(x).float().sum().backward()  # AccumulateGrad adds into the arena slice
     flat.adopt_autograd_grads()
     assert torch.equal(flat.grads, g1)
