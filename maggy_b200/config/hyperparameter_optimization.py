@@ -29,7 +29,10 @@ class HyperparameterOptConfig(LagomConfig):
                  es_min: int = 10, es_policy: Union[str, AbstractEarlyStop] = "median",
                  name: str = "HPOptimization", description: str = "", hb_interval: int = 1,
                  model=None, dataset=None, gpus_per_trial: int = 1, num_workers: Optional[int] = None,
-                 seed: Optional[int] = None):
+                 seed: Optional[int] = None, resume_from: Optional[str] = None):
+        """``resume_from`` (additive, not in the reference — SURVEY.md §5.4): log directory of an earlier run of the
+        same experiment; trials whose ``<trial_id>/trial.json`` is FINALIZED there are not executed again — when the
+        controller suggests the same configuration its saved result is replayed into the stores."""
         super().__init__(name, description, hb_interval)
         if not isinstance(num_trials, int) or isinstance(num_trials, bool) or num_trials <= 0:
             raise ValueError(f"Number of trials should be greater than zero! got {num_trials!r}")
@@ -48,6 +51,7 @@ class HyperparameterOptConfig(LagomConfig):
         self.gpus_per_trial = gpus_per_trial
         self.num_workers = num_workers
         self.seed = seed
+        self.resume_from = resume_from
 
 
 # the docs / notebooks of the reference also use this name (docs/hpo/strategies.md:20)

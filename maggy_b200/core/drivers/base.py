@@ -234,6 +234,12 @@ class Driver(ABC):
     def stop(self) -> None:
         self.worker_done = True
         try:
+            from ...utils import tracing
+
+            tracing.stop()
+        except Exception:  # noqa: BLE001
+            pass
+        try:
             if self.pool is not None:
                 self.pool.shutdown(grace_s=1.0)
         finally:

@@ -25,6 +25,7 @@ from ...optimizer import AbstractOptimizer, Asha, GridSearch, RandomSearch, Sing
 from ...optimizer.bayes import GP, TPE
 from ...searchspace import Searchspace
 from ...trial import Trial
+from ...utils import tracing
 from ..environment.singleton import EnvSing
 from .base import Driver
 
@@ -91,11 +92,14 @@ class HyperparameterOptDriver(Driver):
         self._lookahead = None       # a Trial computed ahead of time
         self._lookahead_thread: Optional[threading.Thread] = None
         self._controller_lock = threading.RLock()
+        self._resumable = self._load_finished_trials(getattr(config, "resume_from", None))
+        self.resumed_trials = 0      # how many suggestions were answered from an earlier run's trial.json
         self.inter_trial_gaps = []   # seconds between a FINAL and the next assignment on that worker
         self.stop_latencies = []     # seconds between the decisive METRIC record and the STOP word
 
     # ------------------------------------------------------------------ hooks
     def _exp_startup_callback(self) -> None:
+        tracing.start(os.path.join(self.log_dir, "trace_driver.json"), "driver")
         try:
             tensorboard._register(self.log_dir)
             tensorboard._write_hparams_config(self.log_dir, self.searchspace)
@@ -202,6 +206,11 @@ class HyperparameterOptDriver(Driver):
             self._idle[worker] = (time.time(), finished_trial)
             return
         self._idle.pop(worker, None)
+        if nxt.trial_id in self._resumable:
+            # experiment-level resume: this configuration already finished in the run we are resuming from
+            done = self._replay_finished(nxt)
+            self._assign_next(worker, done, t_final)
+            return
         self._schedule(worker, nxt)
         if t_final is not None:
             self.inter_trial_gaps.append(time.time() - t_final)
@@ -220,6 +229,44 @@ class HyperparameterOptDriver(Driver):
         trial.status = Trial.RUNNING
         self._assigned[worker] = trial.trial_id
         self._scheduled += 1
+        tracing.instant("assign", worker=worker, trial=trial.trial_id)
+
+    # ------------------------------------------------------------------ resume (additive)
+    def _load_finished_trials(self, path) -> dict:
+        """``{trial_id: Trial}`` for every FINALIZED ``<path>/<trial_id>/trial.json`` of an earlier run."""
+        out = {}
+        if not path:
+            return out
+        import glob
+
+        for f in glob.glob(os.path.join(path, "*", "trial.json")):
+            try:
+                t = Trial.from_json(open(f).read())
+            except Exception:  # noqa: BLE001 - a torn file from a crashed run is simply not resumable
+                continue
+            if t.status == Trial.FINALIZED and t.final_metric is not None:
+                out[t.trial_id] = t
+        self.log(f"resume_from={path}: {len(out)} finished trials can be replayed")
+        return out
+
+    def _replay_finished(self, suggested: Trial) -> Trial:
+        saved = self._resumable.pop(suggested.trial_id)
+        with self._controller_lock, self._store_lock:
+            suggested.status = Trial.FINALIZED
+            suggested.final_metric = saved.final_metric
+            suggested.metric_history = list(saved.metric_history)
+            suggested.step_history = list(saved.step_history)
+            suggested.metric_dict = dict(saved.metric_dict)
+            suggested.early_stop = saved.early_stop
+            suggested.duration = saved.duration
+            self._final_store.append(suggested)
+        self._scheduled += 1
+        self.resumed_trials += 1
+        self._update_result(suggested)
+        self.maggy_log = self._update_maggy_log()
+        self.log(f"replayed trial {suggested.trial_id} from the resumed run: {self.maggy_log}")
+        EnvSing.get_instance().dump(suggested.to_json(), os.path.join(self.log_dir, suggested.trial_id, "trial.json"))
+        return suggested
 
     def _maybe_finish(self):
         if not self._assigned and (self._controller_exhausted or len(self._final_store) >= self.num_trials):
@@ -304,6 +351,7 @@ class HyperparameterOptDriver(Driver):
             self._final_store.append(trial)
             self._trial_store.pop(trial.trial_id, None)
         self._assigned.pop(worker, None)
+        tracing.instant("final", worker=worker, trial=trial.trial_id, metric=trial.final_metric)
         # hand the worker its next trial first, do the bookkeeping while it is already training
         self._assign_next(worker, trial, t_final)
         self._update_result(trial)

@@ -49,6 +49,8 @@ def _preimport():
         pass
 
 
+from ...utils import tracing  # noqa: E402
+
 def call_train_fn(train_fn, available: dict):
     """Inject exactly the keyword arguments train_fn declares (reference trial_executor.py:166-179)."""
     sig = inspect.signature(train_fn)
@@ -92,7 +94,8 @@ def run_one_trial(spec, trial_id, params, reporter, log_dir, gang=None):
     available = {"model": getattr(config, "model", None), "dataset": getattr(config, "dataset", None),
                  "hparams": hparams, "reporter": reporter}
     try:
-        retval = call_train_fn(train_fn, available)
+        with tracing.range(f"trial {trial_id}", params={k: repr(v)[:60] for k, v in printable.items()}):
+            retval = call_train_fn(train_fn, available)
         if isinstance(retval, dict) and spec["optimization_key"] not in retval and len(retval) >= 1 \
                 and spec["optimization_key"] == "Metric":
             # reference: with the default key the first value of the returned dict is the metric
@@ -112,6 +115,7 @@ def run_one_trial(spec, trial_id, params, reporter, log_dir, gang=None):
 
 
 def trial_executor_loop(spec, channel, worker_id, attempt, gang=None):
+    tracing.start(os.path.join(spec["log_dir"], f"trace_worker{worker_id}.json"), f"worker{worker_id}")
     env = EnvSing.get_instance()
     log_dir = spec["log_dir"]
     if gang is not None and not gang.is_leader:

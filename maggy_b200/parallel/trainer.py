@@ -12,6 +12,7 @@ from typing import Callable, Optional
 
 import torch
 
+from ..utils import tracing
 from .arena import FlatParams, FusedAdamW
 
 
@@ -73,7 +74,8 @@ class TrainStep:
             self.load_batch(idx, tgt)
         if self.use_cuda_graph:
             if not self._captured:
-                self._capture()
+                with tracing.range("TrainStep.capture"):
+                    self._capture()
             self.graph.replay()
         else:
             from ..ops import functional as F

@@ -362,3 +362,39 @@ def test_gang_ablation_payload_with_closures(monkeypatch):
 
     res = experiment.lagom(train, AblationConfig(ablation_study=study, direction="max", name="gang_abl", gpus_per_trial=2))
     assert res["num_trials"] == 2 and sorted(res["metric_list"]) == [0.0, 1.0]
+
+
+def train_counted(hparams, reporter):
+    import os
+
+    with open(os.environ["MAGGY_TEST_COUNTER"], "a") as f:
+        f.write("x")
+    acc = 1.0 - abs(hparams["lr"] - 0.3)
+    reporter.broadcast(acc, 0)
+    return acc
+
+
+def test_experiment_resume_replays_finished_trials(tmp_path, monkeypatch):
+    """Additive capability: re-running with ``resume_from=<old run dir>`` does not execute the
+    configurations that already finished there."""
+    counter = tmp_path / "count.txt"
+    counter.write_text("")
+    monkeypatch.setenv("MAGGY_TEST_COUNTER", str(counter))
+    sp = Searchspace(lr=("DOUBLE", [0.0, 1.0]), units=("INTEGER", [8, 64]))
+
+    def cfg(**kw):
+        return HyperparameterOptConfig(num_trials=6, optimizer="randomsearch", searchspace=sp, direction="max",
+                                       es_policy="none", name="resume", seed=11, **kw)
+
+    first = experiment.lagom(train_counted, cfg())
+    assert len(counter.read_text()) == 6
+    old_run = _run_dir()
+    # simulate a crash that lost two trials
+    lost = [d for d in sorted(os.listdir(old_run)) if os.path.isfile(os.path.join(old_run, d, "trial.json"))][:2]
+    for d in lost:
+        os.remove(os.path.join(old_run, d, "trial.json"))
+    second = experiment.lagom(train_counted, cfg(resume_from=old_run))
+    assert len(counter.read_text()) == 6 + 2          # only the two lost configurations ran again
+    assert second["num_trials"] == 6
+    assert sorted(second["metric_list"]) == pytest.approx(sorted(first["metric_list"]))
+    assert second["best_id"] == first["best_id"]
