@@ -43,6 +43,9 @@ class HyperparameterOptDriver(Driver):
     executor_kind = "trial"
     experiment_type = "optimization"
 
+    _resumable: dict = {}   # class-level defaults: subclasses with their own constructor (ablation) never resume
+    resumed_trials = 0
+
     def __init__(self, config, app_id, run_id):
         super().__init__(config, app_id, run_id)
         self._final_store = []
