@@ -32,9 +32,16 @@ def make_train_fn(model_name, batch, steps_per_budget, image, classes, engine="g
         from maggy_b200.models.resnet import resnet50
         from maggy_b200.parallel.trainer import build_trainer
 
+        import time as _t
+
+        t0 = _t.time()
         dev = torch.device("cuda", 0)
         torch.manual_seed(0)
-        model = resnet50(classes, dropout=hparams["dropout"]).to(dev).to(memory_format=torch.channels_last)
+        with torch.device(dev):  # parameters are initialised ON the GPU: no CPU-side randn / host-to-device copies
+            model = resnet50(classes, dropout=hparams["dropout"])
+        model = model.to(memory_format=torch.channels_last)
+        torch.cuda.synchronize()
+        t_model = _t.time() - t0
 
         def loss_fn(m, x, y):
             with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -48,11 +55,19 @@ def make_train_fn(model_name, batch, steps_per_budget, image, classes, engine="g
         step_fn.load_batch(x, y)
         steps = int(hparams.get("budget", 1)) * steps_per_budget
         loss = None
-        for step in range(steps):
+        t1 = _t.time()
+        step_fn()  # first call: warm-up iterations + graph capture (they are training steps too)
+        torch.cuda.synchronize()
+        t_capture = _t.time() - t1
+        t2 = _t.time()
+        for step in range(1, steps):
             loss = step_fn()
             if step % 2 == 1 or step == steps - 1:
                 reporter.broadcast(-loss.detach().float(), step)  # published from the GPU (K8), no .item()
-        return -float(loss)
+        final = -float(step_fn.loss if loss is None else loss)
+        reporter.log(f"TIMING model={t_model:.3f}s trainer+capture={t_capture + (t1 - t0 - t_model):.3f}s "
+                     f"steps({steps - 1})={_t.time() - t2:.3f}s", False)
+        return final
 
     def train_fn(hparams, reporter):
         import torch
@@ -64,9 +79,9 @@ def make_train_fn(model_name, batch, steps_per_budget, image, classes, engine="g
             return train_fn_graph(hparams, reporter)
         torch.manual_seed(0)
         impl = "torch" if engine == "eager" else "native"
-        model = (resnet50(classes, dropout=hparams["dropout"], conv_impl=impl) if model_name == "resnet50"
-                 else resnet18ish(classes, conv_impl=impl))
-        model = model.to(dev)
+        with torch.device(dev):  # initialise on the device (see train_fn_graph)
+            model = (resnet50(classes, dropout=hparams["dropout"], conv_impl=impl) if model_name == "resnet50"
+                     else resnet18ish(classes, conv_impl=impl))
         if dev.type == "cuda":
             model = model.to(memory_format=torch.channels_last)
         opt = torch.optim.SGD(model.parameters(), lr=hparams["lr"], momentum=hparams["momentum"],
@@ -102,10 +117,9 @@ def main():
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--proxy-reference-rpc", action="store_true")
     ap.add_argument("--es", default="median", choices=["median", "none"])
-    ap.add_argument("--engine", default="eager", choices=["graph", "native-eager", "eager"],
-                    help="eager: cuDNN + torch SGD, op by op (what a reference user's train_fn does; the measured "
-                         "default); graph: K7 convs + fused AdamW, whole step as one CUDA graph; native-eager: K7 "
-                         "convs, op by op")
+    ap.add_argument("--engine", default="graph", choices=["graph", "native-eager", "eager"],
+                    help="graph (default): K7 convs + fused AdamW, whole step as one CUDA graph; eager: cuDNN + torch "
+                         "SGD, op by op (what a reference user's train_fn does); native-eager: K7 convs, op by op")
     args = ap.parse_args()
     if args.proxy_reference_rpc:
         os.environ["MAGGY_B200_PROXY_REFERENCE_RPC"] = "1"
