@@ -33,7 +33,8 @@ def make_fns(model_name, batch, seq, steps):
 
         torch.manual_seed(0)
         dev = torch.device("cuda", torch.cuda.current_device())
-        model = hparams["model_function"]()
+        with torch.device(dev):  # initialise the 1.2 B parameters on the GPU, not with CPU randn + H2D copies
+            model = hparams["model_function"]()
         world = dist.get_world_size() if dist.is_initialized() else 1
         rank = dist.get_rank() if dist.is_initialized() else 0
         flat = FlatParams(model, device=dev, world_size=world, rank=rank)

@@ -35,11 +35,13 @@ def make_train_fn(model_name, batch, seq, steps, cpu):
         from maggy_b200.parallel.data_parallel import DataParallel
 
         dev = torch.device("cuda", torch.cuda.current_device())
-        model = DataParallel(BertForMaskedLM(cfg), device=dev) if dist.is_initialized() else None
+        with torch.device(dev):  # parameters are initialised on the GPU
+            model = DataParallel(BertForMaskedLM(cfg), device=dev) if dist.is_initialized() else None
         if model is None:
             from maggy_b200.parallel.arena import FlatParams, FusedAdamW
 
-            net = BertForMaskedLM(cfg)
+            with torch.device(dev):
+                net = BertForMaskedLM(cfg)
             flat = FlatParams(net, device=dev)
             opt = FusedAdamW(flat, lr=hparams["lr"], weight_decay=hparams["wd"])
             fwd = net
