@@ -3,6 +3,11 @@ K7 implicit-GEMM convolutions + ATen BatchNorm adopted into the flat arena + the
 
     python examples/resnet_asha_graph.py            # needs >= 1 B200; one worker per visible GPU
 """
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 from maggy_b200 import Searchspace, experiment
 from maggy_b200.config import HyperparameterOptConfig
 from maggy_b200.optimizer import Asha

@@ -3,6 +3,9 @@
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 examples/zero3_sharded_linear.py
 """
 import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 import torch.distributed as dist
