@@ -1,0 +1,112 @@
+"""Property-based checks (hypothesis) of the search-space encoding, trial ids, ASHA / Hyperband schedules and the
+native split-K heuristic."""
+import ctypes
+import math
+import os
+
+import pytest
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from maggy_b200 import Searchspace
+from maggy_b200.trial import Trial
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@settings(max_examples=60, deadline=None)
+@given(lo=st.floats(-1e3, 1e3), width=st.floats(1e-3, 1e3), ilo=st.integers(-50, 50), iw=st.integers(1, 100),
+       seed=st.integers(0, 2**31 - 1))
+def test_searchspace_samples_stay_in_bounds_and_round_trip(lo, width, ilo, iw, seed):
+    sp = Searchspace(x=("DOUBLE", [lo, lo + width]), n=("INTEGER", [ilo, ilo + iw]),
+                     c=("CATEGORICAL", ["relu", "gelu", "tanh"]))
+    sp.seed(seed)
+    disc = Searchspace(d=("DISCRETE", [1, 2, 4, 8]))
+    disc.seed(seed)
+    assert all(c["d"] in (1, 2, 4, 8) for c in disc.get_random_parameter_values(4))
+    with pytest.raises(NotImplementedError):          # same as the reference: DISCRETE has no numeric encoding
+        disc.transform([2])
+    for cfg in sp.get_random_parameter_values(5):
+        assert lo <= cfg["x"] <= lo + width and ilo <= cfg["n"] <= ilo + iw
+        assert cfg["c"] in ("relu", "gelu", "tanh")
+        for norm in (False, True):
+            enc = sp.transform(sp.dict_to_list(cfg), normalize_categorical=norm)
+            assert all(isinstance(v, (int, float)) for v in enc)
+            assert 0.0 - 1e-9 <= enc[0] <= 1.0 + 1e-9 and 0.0 - 1e-9 <= enc[1] <= 1.0 + 1e-9
+            dec = sp.list_to_dict(sp.inverse_transform(enc, normalize_categorical=norm))
+            assert dec["n"] == cfg["n"] and dec["c"] == cfg["c"]
+            assert math.isclose(dec["x"], cfg["x"], rel_tol=1e-9, abs_tol=1e-6 * max(1.0, abs(width)))
+
+
+@settings(max_examples=100, deadline=None)
+@given(a=st.dictionaries(st.text("abcdefgh", min_size=1, max_size=4), st.one_of(st.integers(-5, 5), st.floats(-1, 1, allow_nan=False)),
+                         min_size=1, max_size=4))
+def test_trial_id_is_a_pure_function_of_the_parameters(a):
+    t1, t2 = Trial(dict(a)), Trial(dict(reversed(list(a.items()))))
+    assert t1.trial_id == t2.trial_id and len(t1.trial_id) == 16
+    assert Trial.from_json(t1.to_json()).trial_id == t1.trial_id
+
+
+@settings(max_examples=40, deadline=None)
+@given(rf=st.integers(2, 4), rmin=st.integers(1, 3), levels=st.integers(1, 3))
+def test_asha_budgets_and_promotion_fraction(rf, rmin, levels):
+    from maggy_b200.optimizer import Asha
+
+    rmax = rmin * rf ** levels
+    asha = Asha(reduction_factor=rf, resource_min=rmin, resource_max=rmax)
+    sp = Searchspace(x=("DOUBLE", [0.0, 1.0]))
+    asha.searchspace, asha.num_trials, asha.direction = sp, rf ** (levels + 1) * 2, "max"
+    asha.trial_store, asha.final_store = {}, []
+    asha.initialize()
+    budgets = [asha.budget_of(r) for r in range(levels + 1)]
+    assert budgets[0] == rmin and budgets[-1] == rmax and budgets == sorted(budgets)
+    # drive it with a synthetic objective: every suggestion finishes immediately with metric = x
+    seen, finished = [], None
+    for _ in range(asha.num_trials * 3):
+        nxt = asha.get_suggestion(finished)
+        if nxt is None:
+            break
+        if nxt == "IDLE":
+            finished = None
+            continue
+        nxt.final_metric = nxt.params["x"]
+        asha.final_store.append(nxt)
+        seen.append(nxt)
+        finished = nxt
+    per_budget = {}
+    for t in seen:
+        per_budget[t.params["budget"]] = per_budget.get(t.params["budget"], 0) + 1
+    assert set(per_budget) <= set(budgets)
+    for lo_b, hi_b in zip(budgets, budgets[1:]):
+        # at most a 1/rf fraction of a rung is ever promoted to the next one
+        assert per_budget.get(hi_b, 0) <= per_budget.get(lo_b, 0) // rf + 1
+
+
+@settings(max_examples=40, deadline=None)
+@given(min_b=st.integers(1, 4), eta=st.integers(2, 4), levels=st.integers(1, 3), iters=st.integers(1, 4))
+def test_hyperband_brackets_are_geometric(min_b, eta, levels, iters):
+    from maggy_b200.pruner import Hyperband
+
+    hb = Hyperband(min_budget=min_b, max_budget=min_b * eta ** levels, eta=eta, n_iterations=iters,
+                   trial_metric_getter=lambda ids: {})
+    assert hb.num_trials() > 0
+    for it in hb.iterations:
+        assert it.budgets == sorted(it.budgets) and it.budgets[-1] == min_b * eta ** levels
+        assert all(b2 == b1 * eta for b1, b2 in zip(it.budgets, it.budgets[1:]))
+        assert it.n_configs == sorted(it.n_configs, reverse=True)
+
+
+def test_native_split_k_heuristic_invariants():
+    lib_path = os.path.join(ROOT, "maggy_b200", "lib", "libmaggy_b200_cuda.so")
+    if not os.path.exists(lib_path):
+        pytest.skip("native library not built")
+    f = ctypes.CDLL(lib_path).mg_gemm_auto_splits
+    f.argtypes, f.restype = [ctypes.c_int] * 4, ctypes.c_int
+    for M in (128, 768, 2304, 3072, 50304, 65536):
+        for N in (64, 768, 3072):
+            for K in (64, 768, 4096, 65536):
+                s = f(M, N, K, 0)
+                assert 1 <= s <= 16
+                if s > 1:
+                    assert (K + 63) // 64 // s >= 16        # at least 1024 of K per split
+                    assert ((M + 127) // 128) * ((N + 255) // 256) * 2 <= 148 or N < 192
