@@ -398,3 +398,23 @@ def test_experiment_resume_replays_finished_trials(tmp_path, monkeypatch):
     assert second["num_trials"] == 6
     assert sorted(second["metric_list"]) == pytest.approx(sorted(first["metric_list"]))
     assert second["best_id"] == first["best_id"]
+
+
+def train_with_poisoned_records(hparams, reporter):
+    """Fault injection (SURVEY.md §5.3 "poison a ring slot"): garbage reaches the driver between valid reports."""
+    ch = reporter.channel
+    ch.lib.mgr_post(ch.h, ch.worker, 99, 0xDEADBEEF, 7, 123.0, 0)            # unknown record type
+    ch.post_metric("00000000deadbeef", 1e9, 3)                               # METRIC for a trial nobody scheduled
+    acc = 1.0 - abs(hparams["lr"] - 0.3)
+    reporter.broadcast(acc, 0)
+    ch.lib.mgr_post(ch.h, ch.worker, 3, 0xDEADBEEF, 0, 5.0, 0)               # FINAL for an unknown trial (no blob)
+    return acc
+
+
+def test_driver_survives_poisoned_records():
+    sp = Searchspace(lr=("DOUBLE", [0.0, 1.0]), units=("INTEGER", [8, 64]))
+    cfg = HyperparameterOptConfig(num_trials=4, optimizer="randomsearch", searchspace=sp, direction="max",
+                                  es_policy="median", es_min=1, name="poison", seed=5)
+    res = experiment.lagom(train_with_poisoned_records, cfg)
+    assert res["num_trials"] == 4 and len(res["metric_list"]) == 4
+    assert all(0.0 <= m <= 1.0 for m in res["metric_list"])                  # the 1e9 / 5.0 garbage never became a result
