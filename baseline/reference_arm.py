@@ -100,6 +100,11 @@ def run(args) -> int:
         import refenv
 
         refenv.install()
+        sys.modules.pop("maggy", None)  # never the repo's own `maggy` alias package
+        import maggy as _ref_pkg
+
+        if not os.path.abspath(_ref_pkg.__file__).startswith(os.path.abspath(ref_dir)):
+            return unavailable(f"`import maggy` resolved to {_ref_pkg.__file__}, not to baseline/_ref")
         from maggy.config import BaseConfig
         from maggy.experiment import experiment as ref_experiment
     except Exception as e:  # noqa: BLE001

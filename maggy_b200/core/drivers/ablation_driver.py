@@ -33,7 +33,9 @@ class AblationDriver(HyperparameterOptDriver):
         self.searchspace = None
         self.optimization_key = getattr(config, "optimization_key", "Metric")
         self.direction = self._init_direction(config.direction)
-        self.earlystop_check = NoStoppingRule
+        self.es_policy = NoStoppingRule
+        self.earlystop_check = NoStoppingRule.earlystop_check
+        self._no_earlystop = True
         self.es_interval, self.es_min = 1, 10 ** 9
         if not isinstance(config.ablation_study, AblationStudy):
             raise Exception(f"The experiment's ablation study configuration should be an instance of "

@@ -68,7 +68,10 @@ class HyperparameterOptDriver(Driver):
         wanted = getattr(config, "num_workers", None)
         pool = wanted or max(1, util.num_executors(default=2) // self.gpus_per_worker)
         self.num_executors = max(1, min(pool, self.num_trials))
-        self.earlystop_check = self._init_earlystop_check(config.es_policy)
+        self.es_policy = self._init_earlystop_check(config.es_policy)
+        # the bound check itself (reference: optimization_driver.py:657-691 returns the policy's static method)
+        self.earlystop_check = self.es_policy.earlystop_check
+        self._no_earlystop = self._policy_is(self.es_policy, NoStoppingRule)
         self.es_interval = config.es_interval
         self.es_min = config.es_min
         self.result = {"best_val": "n.a.", "num_trials": 0, "early_stopped": 0}
@@ -130,8 +133,9 @@ class HyperparameterOptDriver(Driver):
 
     def init(self, job_start: float) -> None:
         super().init(job_start)
-        native_median = isinstance(self.earlystop_check, type) and issubclass(self.earlystop_check, MedianStoppingRule) \
-            or isinstance(self.earlystop_check, MedianStoppingRule)
+        # only the stock median rule is mirrored natively (pump thread / K9); a subclass overriding the check is custom
+        native_median = self._policy_is(self.es_policy, MedianStoppingRule) and \
+            getattr(self.es_policy, "earlystop_check") is MedianStoppingRule.earlystop_check
         self._native_policy = bool(native_median)
         self.channel.configure_policy(self._native_policy, self.direction, self.es_min, self.es_interval)
 
@@ -310,7 +314,7 @@ class HyperparameterOptDriver(Driver):
             trial.set_early_stop()
             self.stop_latencies.append(max(0.0, (self.channel.stop_time_ns(msg["partition_id"]) - msg["t_ns"]) / 1e9))
             return
-        if self._native_policy or new_step is None or trial.get_early_stop():
+        if self._native_policy or self._no_earlystop or new_step is None or trial.get_early_stop():
             return
         with self._store_lock:
             finals = list(self._final_store)
@@ -488,11 +492,16 @@ class HyperparameterOptDriver(Driver):
                         f"is {optimizer} (of type '{type(optimizer).__name__}').")
 
     @staticmethod
+    def _policy_is(policy, cls) -> bool:
+        return isinstance(policy, cls) or (isinstance(policy, type) and issubclass(policy, cls))
+
+    @staticmethod
     def _init_earlystop_check(es_policy):
+        """Resolve ``es_policy`` to a policy class / instance whose ``earlystop_check`` the digest thread calls."""
         if isinstance(es_policy, str):
             key = es_policy.lower()
             if key == "median":
-                return MedianStoppingRule.earlystop_check if False else MedianStoppingRule
+                return MedianStoppingRule
             if key == "none":
                 return NoStoppingRule
             raise Exception(f"The experiment's early stopping policy should either be a string ('median' or 'none') or "

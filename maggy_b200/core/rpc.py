@@ -66,6 +66,7 @@ def _host():
     sig("mgr_base", [P], P)
     sig("mgr_bytes", [P], u64)
     sig("mgr_num_workers", [P], u32)
+    sig("mgr_payload_bytes", [P], u32)
     sig("mgr_now_ns", [], u64)
     sig("mgr_off_dev_ring", [P, u32], u64)
     sig("mgr_off_ctl", [P, u32], u64)
@@ -149,7 +150,12 @@ class DriverChannel:
                 k = self.lib.mgr_read_blob(self.h, r.worker, self._blob, len(self._blob))
                 if k > 0:
                     raw = self._blob.raw[:k]
-                    msg["data"] = raw.decode("utf-8", "replace") if r.type == REC_LOG else cloudpickle.loads(raw)
+                    try:
+                        msg["data"] = raw.decode("utf-8", "replace") if r.type == REC_LOG else cloudpickle.loads(raw)
+                    except Exception as e:  # noqa: BLE001 - one undecodable blob must not lose the popped batch
+                        msg["data"] = None
+                        msg["decode_error"] = f"{type(e).__name__}: {e}"
+
             if msg["type"] == "REG":
                 self.reservations.add({"partition_id": msg["partition_id"], "task_attempt": msg["aux"],
                                        "host_port": f"shm:{self.name}#{msg['partition_id']}",
@@ -229,7 +235,9 @@ class WorkerChannel:
                 if time.time() > deadline:
                     raise OSError(f"could not attach control segment {name}")
                 time.sleep(0.01)
-        self._payload = ctypes.create_string_buffer(1 << 20)
+        # the driver may place payloads up to the segment's slot size (pickled model / dataset closures of an
+        # ablation trial): size the receive buffer from the header, not from a constant
+        self._payload = ctypes.create_string_buffer(max(1 << 16, int(self.lib.mgr_payload_bytes(self.h))))
         self._dev = None  # lazily created device-side producer state
 
     def register(self):

@@ -354,6 +354,8 @@ void mgr_close(void* hv, int unlink_it) {
 void* mgr_base(void* hv) { return static_cast<Handle*>(hv)->base; }
 uint64_t mgr_bytes(void* hv) { return static_cast<Handle*>(hv)->bytes; }
 uint32_t mgr_num_workers(void* hv) { return static_cast<Handle*>(hv)->hdr()->num_workers; }
+// size of one assign / blob slot: workers size their receive buffer from the segment, not from a constant
+uint32_t mgr_payload_bytes(void* hv) { return static_cast<Handle*>(hv)->hdr()->payload_bytes; }
 uint64_t mgr_now_ns() { return now_ns(); }
 
 // byte offsets so the CUDA side (ring_device.cu) can address the same structures after

@@ -22,7 +22,7 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* scrat
 __global__ void __launch_bounds__(1024)
 ce_fwd_bwd_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restrict__ targets,
                   float* __restrict__ losses, int v_real, int v_pad, long long ld,
-                  float grad_scale, int ignore_index) {
+                  float grad_scale, const float* __restrict__ grad_scale_dev, int ignore_index) {
   extern __shared__ __align__(16) uint8_t smem_row[];
   __shared__ float scratch[32];
   uint4* srow = reinterpret_cast<uint4*>(smem_row);
@@ -118,7 +118,8 @@ ce_fwd_bwd_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restric
     if (!ignored) loss = logf(sum) + mx - x_tgt;
     losses[row] = loss;
   }
-  const float gs = ignored ? 0.f : grad_scale;
+  // grad_scale_dev (optional): a device scalar such as 1 / (number of non-ignored rows), known only on the device
+  const float gs = ignored ? 0.f : (grad_scale_dev ? grad_scale * __ldg(grad_scale_dev) : grad_scale);
   for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
     uint4 u = srow[i];
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -158,7 +159,7 @@ ce_fwd_bwd_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restric
 __global__ void __launch_bounds__(1024)
 ce_fwd_bwd_stream_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restrict__ targets,
                          float* __restrict__ losses, int v_real, int v_pad, long long ld, float grad_scale,
-                         int ignore_index) {
+                         const float* __restrict__ grad_scale_dev, int ignore_index) {
   __shared__ float scratch[32];
   const int row = blockIdx.x;
   uint4* grow = reinterpret_cast<uint4*>(logits + static_cast<size_t>(row) * ld);
@@ -205,7 +206,8 @@ ce_fwd_bwd_stream_kernel(__nv_bfloat16* __restrict__ logits, const long long* __
     losses[row] = loss;
   }
   __syncthreads();  // the target logit is read before any thread overwrites the row
-  const float gs = ignored ? 0.f : grad_scale;
+  // grad_scale_dev (optional): a device scalar such as 1 / (number of non-ignored rows), known only on the device
+  const float gs = ignored ? 0.f : (grad_scale_dev ? grad_scale * __ldg(grad_scale_dev) : grad_scale);
   for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
     const uint4 u = grow[i];
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -416,14 +418,15 @@ inline int check() {
 }  // namespace
 
 extern "C" int mg_ce_fwd_bwd(void* logits, const long long* targets, float* losses, int rows,
-                             int v_real, int v_pad, long long ld, float grad_scale,
+                             int v_real, int v_pad, long long ld, float grad_scale, const float* grad_scale_dev,
                              int ignore_index, void* stream) {
   if (v_pad % 8 != 0 || ld % 8 != 0) return -1;
   size_t smem = static_cast<size_t>(v_pad) * 2;
   if (smem > 110 * 1024) {
     // the row would not leave room for two CTAs per SM (or does not fit at all): streaming variant
     ce_fwd_bwd_stream_kernel<<<rows, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<__nv_bfloat16*>(logits), targets, losses, v_real, v_pad, ld, grad_scale, ignore_index);
+        reinterpret_cast<__nv_bfloat16*>(logits), targets, losses, v_real, v_pad, ld, grad_scale, grad_scale_dev,
+        ignore_index);
     return check();
   }
   static size_t configured = 0;
@@ -438,7 +441,7 @@ extern "C" int mg_ce_fwd_bwd(void* logits, const long long* targets, float* loss
   // keep enough 16-byte loads in flight (2 CTAs x 1024 threads per SM at 100 KB/row)
   const int threads = v_pad >= 16384 ? 1024 : (v_pad >= 4096 ? 512 : 256);
   ce_fwd_bwd_kernel<<<rows, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<__nv_bfloat16*>(logits), targets, losses, v_real, v_pad, ld, grad_scale,
+      reinterpret_cast<__nv_bfloat16*>(logits), targets, losses, v_real, v_pad, ld, grad_scale, grad_scale_dev,
       ignore_index);
   return check();
 }

@@ -145,7 +145,7 @@ class GPT2(nn.Module):
         logits = F.linear(x, self.wte)  # tied LM head: [B, T, padded_vocab]
         if targets is None:
             return logits
-        return F.cross_entropy(logits, targets, v_real=self.cfg.vocab_size)
+        return F.cross_entropy(logits, targets, v_real=self.cfg.vocab_size, reduction="mean_all")
 
 
 class TorchGPT2(nn.Module):

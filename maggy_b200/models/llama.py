@@ -118,4 +118,4 @@ class Llama(nn.Module):
         logits = F.linear(x, self.tok if self.lm_head is None else self.lm_head)
         if targets is None:
             return logits
-        return F.cross_entropy(logits, targets, v_real=cfg.vocab_size)
+        return F.cross_entropy(logits, targets, v_real=cfg.vocab_size, reduction="mean_all")

@@ -68,7 +68,7 @@ def cuda():
                                 c_float, c_int, c_float, P, c_float, P, P, P])
         _sig(lib.mg_sumsq_bf16, [P, c_ll, P, P])
         _sig(lib.mg_cast_f32_bf16, [P, P, c_ll, P])
-        _sig(lib.mg_ce_fwd_bwd, [P, P, P, c_int, c_int, c_int, c_ll, c_float, c_int, P])
+        _sig(lib.mg_ce_fwd_bwd, [P, P, P, c_int, c_int, c_int, c_ll, c_float, P, c_int, P])
         _sig(lib.mg_colsum_slabs, [c_int])
         _sig(lib.mg_colsum_bf16, [P, c_int, c_int, c_ll, P, P, c_int, P])
         _sig(lib.mg_gelu_fwd, [P, P, c_ll, P])

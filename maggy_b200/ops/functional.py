@@ -497,23 +497,32 @@ def mlp(x, w1, b1, w2, b2, residual=None):
 
 
 class _CrossEntropy(torch.autograd.Function):
-    """mean NLL over non-ignored rows; the logits buffer is overwritten with its own gradient."""
+    """mean NLL; the logits buffer is overwritten with its own gradient.
+
+    ``count_valid=True`` is torch's ``ignore_index`` semantics (mean over NON-ignored rows): the divisor is counted
+    on the device and handed to the kernel as a device scalar, so no host sync is needed. ``False`` divides by the
+    total row count (identical when no target is ignored, and one reduction cheaper)."""
 
     @staticmethod
-    def forward(ctx, logits, targets, v_real, ignore_index, unit_grad):
+    def forward(ctx, logits, targets, v_real, ignore_index, unit_grad, count_valid):
         l2 = logits.reshape(-1, logits.shape[-1])
         assert l2.stride(1) == 1
         t = targets.reshape(-1)
         rows, v_pad = l2.shape
         losses = torch.empty(rows, dtype=torch.float32, device=logits.device)
+        inv = None
+        if count_valid:
+            valid = ((t != ignore_index) & (t >= 0) & (t < v_real)).sum()
+            inv = valid.clamp_(min=1).to(torch.float32).reciprocal_()
         rc = _lib.cuda().mg_ce_fwd_bwd(l2.data_ptr(), t.data_ptr(), losses.data_ptr(), rows, v_real,
-                                       v_pad, l2.stride(0), 1.0 / rows, ignore_index, _stream())
+                                       v_pad, l2.stride(0), 1.0 if count_valid else 1.0 / rows, _ptr(inv),
+                                       ignore_index, _stream())
         _lib.check(rc, "mg_ce_fwd_bwd")
         _count(1)
         ctx.save_for_backward(l2)
         ctx.lshape = logits.shape
         ctx.unit = unit_grad
-        return losses.sum() / rows
+        return losses.sum() * inv if count_valid else losses.sum() / rows
 
     @staticmethod
     def backward(ctx, dloss):
@@ -522,14 +531,19 @@ class _CrossEntropy(torch.autograd.Function):
         g = dlogits.view(ctx.lshape)
         if not ctx.unit:
             g = g * dloss.to(g.dtype)
-        return g, None, None, None, None
+        return g, None, None, None, None, None
 
 
-def cross_entropy(logits, targets, v_real=None, ignore_index=-100, unit_grad=True):
-    """Fused softmax-CE (mean over rows). NOTE: consumes ``logits`` (overwritten by d loss/d logits).
+def cross_entropy(logits, targets, v_real=None, ignore_index=-100, unit_grad=True, reduction="mean"):
+    """Fused softmax-CE. NOTE: consumes ``logits`` (overwritten by d loss/d logits).
 
-    ``unit_grad=True`` assumes the loss is the root of backward (upstream gradient == 1)."""
-    return _CrossEntropy.apply(logits, targets, v_real or logits.shape[-1], ignore_index, unit_grad)
+    ``reduction="mean"`` averages over the rows whose target is not ``ignore_index`` (torch semantics);
+    ``"mean_all"`` divides by the total row count — the same number when nothing is ignored (causal-LM training),
+    without the device-side count. ``unit_grad=True`` assumes the loss is the root of backward."""
+    if reduction not in ("mean", "mean_all"):
+        raise ValueError(f"reduction must be 'mean' or 'mean_all', got {reduction!r}")
+    return _CrossEntropy.apply(logits, targets, v_real or logits.shape[-1], ignore_index, unit_grad,
+                               reduction == "mean")
 
 
 class _Embedding(torch.autograd.Function):

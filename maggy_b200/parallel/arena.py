@@ -262,12 +262,21 @@ class FusedAdamW:
             F._count(1)
         flat.start_step()
 
+    def current_step(self) -> int:
+        """Number of optimizer steps taken. Under CUDA-graph replay only the device counter advances (the host
+        ``step_count`` freezes at its capture-time value), so the device tensor is the source of truth there."""
+        if self.graph_safe and getattr(self, "step_tensor", None) is not None:
+            return int(self.step_tensor.item())
+        return int(self.step_count)
+
     def state_dict(self):
-        return {"step": self.step_count, "m": self.m, "v": self.v, "master": self.flat.master,
+        return {"step": self.current_step(), "m": self.m, "v": self.v, "master": self.flat.master,
                 "rank": self.flat.rank, "world_size": self.flat.world_size}
 
     def load_state_dict(self, sd):
         self.step_count = int(sd["step"])
+        if getattr(self, "step_tensor", None) is not None:
+            self.step_tensor.fill_(int(sd["step"]))
         self.m.copy_(sd["m"])
         self.v.copy_(sd["v"])
         self.flat.master.copy_(sd["master"])

@@ -33,6 +33,10 @@ def save_training_state(directory: str, flat, opt, extra: Optional[dict] = None)
                os.path.join(directory, f"optim_rank{flat.rank}.pt"))
     if flat.rank == 0:
         torch.save(flat.params.detach().cpu(), os.path.join(directory, "params.pt"))
+    if flat.world_size > 1 and torch.distributed.is_initialized():
+        # meta.json = "checkpoint complete": every rank's optimizer shard must be on disk before rank 0 writes it
+        torch.distributed.barrier(group=getattr(flat, "group", None))
+    if flat.rank == 0:
         meta = {"format": 1, "step": int(sd["step"]), "geometry": _geometry(flat), "extra": extra or {}}
         tmp = os.path.join(directory, "meta.json.tmp")
         with open(tmp, "w") as f:

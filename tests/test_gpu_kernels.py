@@ -168,12 +168,29 @@ def test_cross_entropy(F):
     ref = torch.nn.functional.cross_entropy(lr, tgt, ignore_index=-100, reduction="sum") / rows
     ref.backward()
     work = logits.clone().requires_grad_(True)
-    loss = F.cross_entropy(work, tgt, v_real=v_real)
+    loss = F.cross_entropy(work, tgt, v_real=v_real, reduction="mean_all")
     assert abs(loss.item() - ref.item()) < 2e-2 * abs(ref.item())
     loss.backward()
     g = work.grad
     assert _rel_err(g[:, :v_real], lr.grad) < 1e-2
     assert g[:, v_real:].abs().max().item() == 0.0
+
+
+def test_cross_entropy_mean_over_valid_rows_matches_torch(F):
+    """Default reduction = torch's ignore_index semantics (BERT-MLM-style labels, mostly -100)."""
+    torch.manual_seed(6)
+    rows, v_real, v_pad = 256, 1000, 1024
+    logits = torch.randn(rows, v_pad, device=DEV, dtype=torch.bfloat16) * 3
+    tgt = torch.randint(0, v_real, (rows,), device=DEV)
+    tgt[torch.rand(rows, device=DEV) < 0.85] = -100
+    lr = logits[:, :v_real].float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lr, tgt, ignore_index=-100)
+    ref.backward()
+    work = logits.clone().requires_grad_(True)
+    loss = F.cross_entropy(work, tgt, v_real=v_real)
+    assert abs(loss.item() - ref.item()) < 2e-2 * abs(ref.item())
+    loss.backward()
+    assert _rel_err(work.grad[:, :v_real], lr.grad) < 1e-2
 
 
 def test_cross_entropy_large_vocab_streaming_path(F):
@@ -187,7 +204,7 @@ def test_cross_entropy_large_vocab_streaming_path(F):
     ref = torch.nn.functional.cross_entropy(lr, tgt, ignore_index=-100, reduction="sum") / rows
     ref.backward()
     work = logits.clone().requires_grad_(True)
-    loss = F.cross_entropy(work, tgt, v_real=v_real)
+    loss = F.cross_entropy(work, tgt, v_real=v_real, reduction="mean_all")
     assert abs(loss.item() - ref.item()) < 2e-2 * abs(ref.item())
     loss.backward()
     assert _rel_err(work.grad, lr.grad) < 1e-2

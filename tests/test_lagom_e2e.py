@@ -102,6 +102,52 @@ def test_median_early_stopping_cuts_bad_trials_short():
     assert time.time() - t0 < 60
 
 
+class _StopBelowHalf(__import__("maggy_b200.earlystop", fromlist=["AbstractEarlyStop"]).AbstractEarlyStop):
+    """Custom policy: stop every trial whose constant quality is below 0.5 (the reference accepts instances and
+    classes alike: optimization_driver.py:657-691)."""
+
+    @staticmethod
+    def earlystop_check(to_check, finalized_trials, direction):
+        return to_check.trial_id if to_check.metric_history and to_check.metric_history[-1] < 0.5 else None
+
+
+@pytest.mark.parametrize("as_instance", [True, False])
+def test_custom_early_stop_policy_fires(as_instance):
+    sp = Searchspace(q=("DOUBLE", [0.0, 1.0]))
+    policy = _StopBelowHalf() if as_instance else _StopBelowHalf
+    cfg = OptimizationConfig(num_trials=10, optimizer="randomsearch", searchspace=sp, direction="max",
+                             es_policy=policy, es_interval=1, es_min=1, name="es_custom", seed=5)
+    res = experiment.lagom(train_slow_when_bad, cfg)
+    assert res["num_trials"] == 10
+    run = _run_dir()
+    n_bad_late = n_stopped = 0
+    for tid in os.listdir(run):
+        pth = os.path.join(run, tid, "trial.json")
+        if os.path.exists(pth):
+            t = json.load(open(pth))
+            n_stopped += bool(t["early_stop"])
+            if t["early_stop"]:
+                assert t["metric_history"][-1] < 0.5
+    assert n_stopped >= 1 and res["early_stopped"] == n_stopped
+    assert "takes no arguments" not in open(os.path.join(run, "maggy.log")).read()
+
+
+def test_no_stopping_rule_is_silent():
+    sp = Searchspace(q=("DOUBLE", [0.0, 1.0]))
+    cfg = OptimizationConfig(num_trials=6, optimizer="randomsearch", searchspace=sp, direction="max",
+                             es_policy="none", es_interval=1, es_min=1, name="es_none", seed=5)
+    res = experiment.lagom(train_quadratic_q, cfg)
+    assert res["early_stopped"] == 0
+    log = open(os.path.join(_run_dir(), "maggy.log")).read()
+    assert "takes no arguments" not in log and "Trials to stop" not in log
+
+
+def train_quadratic_q(hparams, reporter):
+    for i in range(6):
+        reporter.broadcast(hparams["q"], i)
+    return hparams["q"]
+
+
 def test_asha_and_gridsearch_run():
     sp = Searchspace(lr=("DOUBLE", [0.0, 1.0]), units=("INTEGER", [8, 64]))
     from maggy_b200.optimizer import Asha
