@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--attn", default="", choices=["", "sdpa", "native"],
-                    help="attention implementation of the model (default: MAGGY_B200_ATTN or sdpa)")
+                    help="attention implementation of the model (default: MAGGY_B200_ATTN or native = K10)")
     ap.add_argument("--no-multicast", action="store_true", help="force the peer load/store variant of the fused kernel")
     ap.add_argument("--multicast", action="store_true", help="force the NVSwitch multimem variant (default: auto)")
     return ap.parse_args()
@@ -217,7 +217,7 @@ def main():
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic random tokens, random-init weights",
         "impl": args.impl,
-        "config": {"attention": (args.attn or os.environ.get("MAGGY_B200_ATTN", "sdpa")) if args.impl == "ours" else "sdpa",
+        "config": {"attention": (args.attn or os.environ.get("MAGGY_B200_ATTN", "native")) if args.impl == "ours" else "sdpa",
                    "model": args.model, "params": sum(p.numel() for p in model.parameters()) if args.impl == "ours" else None,
                    "global_batch": B * world, "seq_len": T, "per_gpu_batch": B,
                    "parallelism": f"dp{world}" + ("+zero1-fused-rs-adam" if args.impl == "ours" else "+ddp+zero1"),

@@ -17,46 +17,23 @@
 //                             second MMA. O accumulates IN TMEM across key tiles (MMA accumulate) relative to a lazily
 //                             updated reference max: it is only rescaled in place (tcgen05.ld / .st) when a row's max
 //                             grows by more than 2^8, which after the first tiles almost never happens
-#include "../include/mg_ptx.cuh"
+#include "../include/mg_attn.cuh"
 
 #include <cstdio>
-#include <mutex>
+#include <cstdlib>
 #include <type_traits>
+
+// tuned generation (attention_v2.cu); this file's kernels stay as the reference implementation (MAGGY_B200_ATTN_GEN=1)
+extern "C" int mg_attn_fwd_v2(const void* qkv, void* o, float* lse, int B, int T, int H, int KVH, int causal, float scale,
+                              void* stream);
+extern "C" int mg_attn_bwd_v2(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv,
+                              float* delta, float* dq_acc, int B, int T, int H, int KVH, int causal, float scale,
+                              void* stream);
 
 namespace {
 
 using namespace mg;
-
-constexpr int kD = 64;        // head dim
-constexpr int kBQ = 128;      // query rows per tile
-constexpr int kTile = 128 * 128;  // bytes of a [128 rows x 64 bf16] tile
-
-struct AttnParams {
-  int B, T, H, KVH;     // batch, sequence, query heads, key/value heads
-  int Cq, Ckv;          // H*64, KVH*64
-  int causal;
-  float scale_log2;     // softmax scale * log2(e)
-  float* lse;           // [B, H, T] log2-domain log-sum-exp of the scaled scores
-  // backward only
-  const float* delta;   // [B, H, T] rowsum(dO * O)
-  float* dq_acc;        // [B, T, Cq] fp32
-};
-
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-               : "memory");
-}
-
-__device__ __forceinline__ uint4 pack8(const float* v) {
-  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                    pack_bf16x2(v[6], v[7]));
-}
+using namespace mg::attn;
 
 // ------------------------------------------------------------------------------------------------
 // forward
@@ -706,38 +683,31 @@ __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloa
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-PFN_encodeTiled encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
-  });
-  return fn;
-}
-
-// [B, T, C] bf16 (row stride `ld` elements) as a 3-D map {C, T, B}; box {64, box_rows, 1}; 128B swizzle
-int make_map_btc(CUtensorMap* map, const void* ptr, int B, int T, int C, long long ld, int box_rows = 128) {
-  PFN_encodeTiled enc = encode_fn();
-  if (!enc) return -100;
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(ld) * 2 * T};
-  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : -200 - static_cast<int>(r);
-}
-
 }  // namespace
+
+namespace mg {
+namespace attn {
+void launch_delta(const void* o, const void* d_o, float* delta, int B, int T, int H, cudaStream_t s) {
+  const long long groups = static_cast<long long>(B) * T * H;
+  const long long blocks = (groups * 8 + 255) / 256;
+  attn_delta_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o),
+                                                                  static_cast<const __nv_bfloat16*>(d_o), delta, B, T, H);
+}
+void launch_dq_convert(const float* dq_acc, void* dqkv, long long rows, int Cq, int ld, float scale, cudaStream_t s) {
+  long long blocks = (rows * (Cq / 8) + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  attn_dq_convert_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(dq_acc, static_cast<__nv_bfloat16*>(dqkv), rows, Cq,
+                                                                       ld, scale);
+}
+int generation() {
+  static int gen = [] {
+    const char* e = getenv("MAGGY_B200_ATTN_GEN");
+    return e ? atoi(e) : 2;
+  }();
+  return gen;
+}
+}  // namespace attn
+}  // namespace mg
 
 extern "C" {
 
@@ -746,6 +716,7 @@ extern "C" {
 int mg_attn_fwd(const void* qkv, void* o, float* lse, int B, int T, int H, int KVH, int causal, float scale,
                 void* stream) {
   if (B <= 0 || T <= 0 || H <= 0 || KVH <= 0 || H % KVH != 0) return -1;
+  if (mg::attn::generation() >= 2) return mg_attn_fwd_v2(qkv, o, lse, B, T, H, KVH, causal, scale, stream);
   AttnParams p;
   p.B = B; p.T = T; p.H = H; p.KVH = KVH;
   p.Cq = H * kD; p.Ckv = KVH * kD;
@@ -781,6 +752,8 @@ int mg_attn_fwd(const void* qkv, void* o, float* lse, int B, int T, int H, int K
 int mg_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, float* delta,
                 float* dq_acc, int B, int T, int H, int KVH, int causal, float scale, void* stream) {
   if (B <= 0 || T <= 0 || H <= 0 || KVH <= 0 || H % KVH != 0) return -1;
+  if (mg::attn::generation() >= 2)
+    return mg_attn_bwd_v2(qkv, o, d_o, lse, dqkv, delta, dq_acc, B, T, H, KVH, causal, scale, stream);
   AttnParams p;
   p.B = B; p.T = T; p.H = H; p.KVH = KVH;
   p.Cq = H * kD; p.Ckv = KVH * kD;

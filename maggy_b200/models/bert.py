@@ -32,6 +32,9 @@ class BertConfig:
         return cls(**table[name])
 
 
+from .gpt2 import _attn_impl  # noqa: E402
+
+
 class BertLayer(nn.Module):
     def __init__(self, cfg: BertConfig):
         super().__init__()
@@ -49,11 +52,14 @@ class BertLayer(nn.Module):
     def forward(self, x, attn_mask=None):
         B, T, C = x.shape
         H = self.n_heads
-        qkv = F.linear(x, self.qkv_w, self.qkv_b).view(B, T, 3, H, C // H)
-        q, k, v = qkv.unbind(dim=2)
-        y = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
-                                                             attn_mask=attn_mask)
-        y = y.transpose(1, 2).reshape(B, T, C)
+        qkv = F.linear(x, self.qkv_w, self.qkv_b)
+        if attn_mask is None and C // H == 64 and x.is_cuda and _attn_impl(None) == "native":
+            y = F.attention(qkv, H, causal=False)   # K10, bidirectional
+        else:
+            q, k, v = qkv.view(B, T, 3, H, C // H).unbind(dim=2)
+            y = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2),
+                                                                 v.transpose(1, 2), attn_mask=attn_mask)
+            y = y.transpose(1, 2).reshape(B, T, C)
         x = F.layer_norm(F.linear(y, self.o_w, self.o_b, residual=x), self.ln1_w, self.ln1_b, self.eps)
         x = F.layer_norm(F.mlp(x, self.fc_w, self.fc_b, self.fc2_w, self.fc2_b, residual=x), self.ln2_w, self.ln2_b,
                          self.eps)

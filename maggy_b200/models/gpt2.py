@@ -29,7 +29,7 @@ class GPT2Config:
     n_embd: int = 768
     padded_vocab_size: int = 0  # 0 -> round vocab up to a multiple of 128 (tile / vector friendly)
     layer_norm_eps: float = 1e-5
-    attn_impl: str = ""  # "" -> MAGGY_B200_ATTN or "sdpa"; "native" = maggy_b200 tcgen05 attention (K10)
+    attn_impl: str = ""  # "" -> MAGGY_B200_ATTN or "native" (maggy_b200 tcgen05 attention, K10); "sdpa" = torch SDPA
 
     def __post_init__(self):
         if self.padded_vocab_size == 0:
@@ -48,12 +48,12 @@ class GPT2Config:
 
 
 def _attn_impl(cfg) -> str:
-    """"native": the maggy_b200 tcgen05 attention kernels (K10); "sdpa": torch SDPA (cuDNN flash attention).
-    Measured on B200 (profiles/attention.md) the library kernel is still faster (forward 0.72x, backward 0.5x), so
-    "sdpa" is the default for the throughput benchmark; MAGGY_B200_ATTN=native / cfg.attn_impl select ours."""
+    """"native" (default): the maggy_b200 tcgen05 attention kernels (K10, csrc/ops/attention_v2.cu) — no library kernel
+    is left in the training step. "sdpa": torch SDPA (cuDNN flash attention), kept as a comparison arm only
+    (MAGGY_B200_ATTN=sdpa / cfg.attn_impl="sdpa"); numbers for both in profiles/attention.md."""
     import os
 
-    return getattr(cfg, "attn_impl", None) or os.environ.get("MAGGY_B200_ATTN", "sdpa")
+    return getattr(cfg, "attn_impl", None) or os.environ.get("MAGGY_B200_ATTN", "native")
 
 
 class Block(nn.Module):

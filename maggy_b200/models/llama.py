@@ -51,6 +51,9 @@ def apply_rope(x, cos, sin):
     return out.to(x.dtype)
 
 
+from .gpt2 import _attn_impl  # noqa: E402  (MAGGY_B200_ATTN / cfg.attn_impl, default "native")
+
+
 class LlamaBlock(nn.Module):
     def __init__(self, cfg: LlamaConfig):
         super().__init__()
@@ -74,9 +77,15 @@ class LlamaBlock(nn.Module):
         q = apply_rope(q.view(B, T, H, hd), cos, sin)
         k = apply_rope(k.view(B, T, KV, hd), cos, sin)
         v = v.view(B, T, KV, hd)
-        y = torch.nn.functional.scaled_dot_product_attention(
-            q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True, enable_gqa=True)
-        x = F.linear(y.transpose(1, 2).reshape(B, T, C), self.wo, residual=x)
+        if hd == 64 and x.is_cuda and _attn_impl(cfg) == "native":
+            # K10 reads q / k / v out of one fused [B, T, (H + 2 KV) * 64] buffer (grouped-query aware)
+            y = F.attention(torch.cat([q.reshape(B, T, H * hd), k.reshape(B, T, KV * hd), v.reshape(B, T, KV * hd)],
+                                      dim=-1), H, KV, causal=True)
+        else:
+            y = torch.nn.functional.scaled_dot_product_attention(
+                q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True, enable_gqa=True)
+            y = y.transpose(1, 2).reshape(B, T, C)
+        x = F.linear(y, self.wo, residual=x)
         h = F.rms_norm(x, self.ffn_norm, cfg.norm_eps)
         gate, up = lin(h, self.w13).chunk(2, dim=-1)
         x = F.linear(torch.nn.functional.silu(gate) * up, self.w2, residual=x)
