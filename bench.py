@@ -4,13 +4,19 @@
 Contract (see task statement): ``python bench.py --gpus N --steps K --warmup W`` — for N > 1 it is
 launched under ``torch.distributed.run`` with one rank per GPU. Prints ONE JSON line on rank 0.
 
+Both arms go through the product's public entry point: every torchrun rank calls ``experiment.lagom(train_fn,
+BaseConfig(...))`` (ours: ``maggy_b200.experiment.lagom``; ``--impl reference``: the unmodified reference's
+``maggy.experiment.lagom`` from ``baseline/_ref``, see ``baseline/reference_arm.py`` and DESIGN.md section 5) and the
+oblivious ``train_fn`` builds the model, trains and reports through ``reporter.broadcast``.
+
 * ``value``   device-timed (CUDA events, max over ranks) whole-job tokens/s of the full training step:
               forward + backward + fused reduce-scatter/AdamW/all-gather, replayed as a CUDA graph.
-* ``e2e``     the same metric through the public API (``TrainStep.__call__``) including, every step, the
-              pinned-host -> device copy of that step's batch and a device -> host read of the loss.
-* ``--impl reference`` runs the unmodified reference from ``baseline/_ref`` if it can be imported
-              (it cannot in this image: it imports tensorflow/pyspark unconditionally) and otherwise
-              reports ``unavailable``.
+* ``e2e``     the same metric through the public API including, every step, the pinned-host -> device copy of that
+              step's batch, a device -> host read of the loss and ``reporter.broadcast(loss, step)``.
+* guards      at N > 1, before timing: parameters bit-identical on every rank after the warm-up steps (the fused
+              kernel's all-gather epilogue) and a finite loss; the line carries ``grad_dtype``.
+* ``--config asha``  BASELINE config 2 (ASHA over ResNet-50, one trial per GPU): trials/hour through
+              ``lagom(HyperparameterOptConfig)`` — ``bench/hpo_asha_resnet.py``.
 """
 from __future__ import annotations
 
@@ -41,6 +47,10 @@ def parse_args():
                     help="attention implementation of the model (default: MAGGY_B200_ATTN or native = K10)")
     ap.add_argument("--no-multicast", action="store_true", help="force the peer load/store variant of the fused kernel")
     ap.add_argument("--multicast", action="store_true", help="force the NVSwitch multimem variant (default: auto)")
+    ap.add_argument("--config", default="gpt2-dp", choices=["gpt2-dp", "asha"],
+                    help="gpt2-dp: BASELINE config 3 (headline); asha: BASELINE config 2, trials/hour")
+    ap.add_argument("--trials", type=int, default=64, help="--config asha: number of trials")
+    ap.add_argument("--steps-per-budget", type=int, default=200, help="--config asha: training steps per budget unit")
     return ap.parse_args()
 
 
@@ -111,11 +121,56 @@ def reference_arm(args):
     return ra.run(args)
 
 
+def asha_config(args):
+    """BASELINE config 2 through ``lagom(HyperparameterOptConfig(optimizer=Asha))``: one line of JSON, trials/hour."""
+    cmd = [sys.executable, os.path.join(ROOT, "bench", "hpo_asha_resnet.py"), "--workers", str(args.gpus),
+           "--trials", str(args.trials), "--steps-per-budget", str(args.steps_per_budget), "--batch", str(min(args.batch, 64))]
+    if args.impl == "reference":
+        # the reference's HPO driver needs Spark (maggy/config/hyperparameter_optimization.py:78-81): labelled proxy
+        cmd += ["--proxy-reference-rpc", "--engine", "eager"]
+    return subprocess.call(cmd)
+
+
 def main():
     args = parse_args()
+    if args.config == "asha":
+        return asha_config(args)
     if args.impl == "reference":
         return reference_arm(args)
+    if args.impl == "ours":
+        return ours_through_lagom(args)
+    return run_training(args, reporter=None)
 
+
+def ours_through_lagom(args):
+    """The product path: ``experiment.lagom(train_fn, BaseConfig)`` on every torchrun rank (the same shape as the
+    reference arm: its python driver also runs the oblivious train_fn in-process on each rank)."""
+    import tempfile
+
+    rank = int(os.environ.get("RANK", "0"))
+    os.environ.setdefault("MAGGY_LOG_DIR", tempfile.mkdtemp(prefix=f"maggy_b200_bench_rank{rank}_"))
+    from maggy_b200 import experiment
+    from maggy_b200.config import BaseConfig
+
+    def train_fn(reporter):
+        return run_training(args, reporter=reporter)
+
+    import contextlib
+    import io
+
+    sink = io.StringIO()  # the driver prints its own summary; the contract is ONE JSON line on stdout
+    with contextlib.redirect_stdout(sink if rank == 0 else io.StringIO()):
+        result = experiment.lagom(train_fn, BaseConfig(name="bench_gpt2_dp", description="BASELINE config 3"))
+    line = getattr(run_training, "json_line", None)
+    if rank == 0:
+        if line is None:
+            print(json.dumps({"impl": "ours", "error": "train_fn produced no result", "lagom_result": str(result)[:200]}))
+            return 1
+        print(line)
+    return 0
+
+
+def run_training(args, reporter=None):
     import torch
     import torch.distributed as dist
 
@@ -165,6 +220,23 @@ def main():
         step()
     sync_all()
 
+    # ---------------- correctness guards (untimed) --------------------------
+    guards = {"grad_dtype": str(flat.grads.dtype).replace("torch.", "") if args.impl == "ours" else "float32"}
+    if args.impl == "ours":
+        guards["loss_finite_after_warmup"] = bool(torch.isfinite(step.loss).item())
+        if world > 1:
+            # the fused kernel's all-gather epilogue must leave every rank with the same bf16 parameters, bit for bit
+            words = flat.params.detach().view(torch.int16).to(torch.int64)
+            chk = torch.stack([words.sum(), (words * (torch.arange(words.numel(), device=device) % 8191 + 1)).sum()])
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            guards["params_bit_identical_across_ranks"] = bool((lo == hi).all().item())
+            if not guards["params_bit_identical_across_ranks"]:
+                raise RuntimeError("bench guard: parameters differ between ranks after the warm-up steps")
+        if not guards["loss_finite_after_warmup"]:
+            raise RuntimeError("bench guard: non-finite loss after warm-up")
+
     # ---------------- device-timed region: exactly K steps -----------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -194,6 +266,8 @@ def main():
         idx, tgt = pool[i % len(pool)]
         loss = step(idx, tgt)          # pinned H2D copy + graph replay
         host_losses.append(float(loss.item()))  # D2H read of the step's result
+        if reporter is not None:
+            reporter.broadcast(host_losses[-1], i)
     f1.record()
     sync_all()
     ms_e2e = f0.elapsed_time(f1)
@@ -228,6 +302,9 @@ def main():
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "final_loss": final_loss,
+        "guards": guards,
+        "api": "maggy_b200.experiment.lagom(train_fn, BaseConfig) per rank; reporter.broadcast(loss, step) in the e2e "
+               "region" if reporter is not None else "engine-internal proxy (no lagom)",
         "mfu_vs_measured_bf16_peak": None,
     }
     try:
@@ -238,12 +315,13 @@ def main():
             out["model_tflops_per_gpu"] = fl / 1e12
     except Exception:
         pass
-    if rank == 0:
-        print(json.dumps(out))
+    run_training.json_line = json.dumps(out)
+    if rank == 0 and reporter is None:
+        print(run_training.json_line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return {"tokens_per_sec": value} if reporter is not None else 0
 
 
 def build_torch_baseline(cfg, B, T, device, world, rank):

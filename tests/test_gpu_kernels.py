@@ -319,6 +319,51 @@ def test_gpt2_step_matches_torch():
     assert abs(losses[-1] - rlosses[-1]) < 0.15, (losses, rlosses)
 
 
+def test_gpt2_small_50_step_loss_parity_with_fp32_master_twin():
+    """GPT-2 small (the benchmarked architecture), 50 optimizer steps: the native engine (tcgen05 GEMMs, K10 attention,
+    fused norms / CE / AdamW on a bf16 arena with fp32 master shards) tracks a plain-PyTorch twin that starts from the
+    SAME weights (copied, fp32 parameters under bf16 autocast, torch.optim.AdamW with the same decay grouping)."""
+    from maggy_b200.models.gpt2 import GPT2, GPT2Config, TorchGPT2
+    from maggy_b200.parallel.arena import FlatParams, FusedAdamW
+
+    cfg = GPT2Config.named("gpt2-small")
+    B, T, steps = 4, 512, 50
+    torch.manual_seed(0)
+    model = GPT2(cfg)
+    flat = FlatParams(model, device=DEV)
+    opt = FusedAdamW(flat, lr=3e-4, weight_decay=0.1)
+    ref = TorchGPT2(cfg).to(DEV)
+    with torch.no_grad():
+        src = dict(model.named_parameters())
+        for name, p in ref.inner.named_parameters():
+            p.copy_(src[name].detach().float())
+    ropt = torch.optim.AdamW(
+        [{"params": [p for p in ref.parameters() if p.dim() >= 2], "weight_decay": 0.1},
+         {"params": [p for p in ref.parameters() if p.dim() < 2], "weight_decay": 0.0}],
+        lr=3e-4, betas=(0.9, 0.95), eps=1e-8)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    batches = [(torch.randint(0, cfg.vocab_size, (B, T), generator=g).to(DEV),
+                torch.randint(0, cfg.vocab_size, (B, T), generator=g).to(DEV)) for _ in range(4)]
+    losses, rlosses = [], []
+    for i in range(steps):
+        idx, tgt = batches[i % 4]
+        opt.zero_grad()
+        loss = model(idx, tgt)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+        ropt.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            rl = ref(idx, tgt)
+        rl.backward()
+        ropt.step()
+        rlosses.append(rl.item())
+    diffs = [abs(a - b) for a, b in zip(losses, rlosses)]
+    assert abs(losses[0] - rlosses[0]) < 0.03, (losses[0], rlosses[0])          # same weights, same batch
+    assert losses[-1] < losses[0] - 1.0 and rlosses[-1] < rlosses[0] - 1.0        # both memorise the 4 batches
+    assert sum(diffs) / len(diffs) < 0.08 and max(diffs) < 0.3, (max(diffs), losses[-5:], rlosses[-5:])
+
+
 def test_train_step_cuda_graph_matches_eager():
     from maggy_b200.models.gpt2 import GPT2Config
     from maggy_b200.parallel.trainer import build_gpt2_trainer
