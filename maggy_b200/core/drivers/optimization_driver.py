@@ -137,7 +137,64 @@ class HyperparameterOptDriver(Driver):
         native_median = self._policy_is(self.es_policy, MedianStoppingRule) and \
             getattr(self.es_policy, "earlystop_check") is MedianStoppingRule.earlystop_check
         self._native_policy = bool(native_median)
-        self.channel.configure_policy(self._native_policy, self.direction, self.es_min, self.es_interval)
+        # MAGGY_B200_HOST_POLICY=0 leaves the device scheduler as the only native engine (tests prove K9 alone suffices)
+        host_engine = self._native_policy and os.environ.get("MAGGY_B200_HOST_POLICY", "1") != "0"
+        self.channel.configure_policy(host_engine, self.direction, self.es_min, self.es_interval)
+        self.device_scheduler = None
+        self.device_scheduler_stats = None
+        self._start_device_scheduler()
+
+    def _start_device_scheduler(self) -> None:
+        """K9: when the workers run on GPUs and the policy is device-decidable, a persistent scheduler kernel takes
+        the early-stop decisions (reference mechanism: heartbeat METRIC -> STOP reply, maggy/core/rpc.py:716-737,
+        447-461) out of a peer-visible mailbox in its own GPU's memory; the host engines keep running — STOP is
+        idempotent.
+
+        Placement: a persistent kernel in the DRIVER's CUDA context time-slices with whatever context trains on the
+        same GPU (no MPS here: contexts of different processes never run side by side), which would halve that
+        worker's throughput. ``MAGGY_B200_DEVICE_SCHED=auto`` (default) therefore starts K9 only when a GPU is left
+        over after the workers took theirs (GPU ``num_executors * gpus_per_worker``); ``=1`` forces it onto cuda:0
+        (used by the tests and by single-GPU debugging), ``=0`` disables it."""
+        mode = os.environ.get("MAGGY_B200_DEVICE_SCHED", "auto").lower()
+        if not self._native_policy or mode in ("0", "off", "false") or self.num_executors > 32:
+            return
+        try:
+            import torch
+
+            ngpu = util.num_physical_devices() if torch.cuda.is_available() else 0
+            taken = self.num_executors * max(1, getattr(self, "gpus_per_worker", 1))
+            if ngpu < 1:
+                return
+            if mode in ("1", "on", "true", "force"):
+                dev = min(taken, ngpu - 1) if ngpu > taken else 0
+            elif ngpu > taken:
+                dev = taken
+            else:
+                self.log("device scheduler (K9) not started: no GPU left over after the workers' "
+                         f"({ngpu} visible, {taken} taken); the native host engine decides. MAGGY_B200_DEVICE_SCHED=1 forces it.")
+                return
+            from ..sched_kernel import DeviceScheduler
+
+            self.device_scheduler = DeviceScheduler(self.channel, direction=self.direction, es_min=self.es_min,
+                                                    es_interval=self.es_interval, device=f"cuda:{dev}").start()
+            self.log(f"device scheduler (K9) running on cuda:{dev}, "
+                     f"mailbox={'yes' if self.device_scheduler.mailbox else 'no'}")
+        except Exception as e:  # noqa: BLE001 - the host policy engine covers every decision on its own
+            self.device_scheduler = None
+            self.log(f"device scheduler not started: {type(e).__name__}: {e}")
+
+    def stop(self) -> None:
+        self._stop_device_scheduler()  # the kernel polls the segment: it must retire before the segment is unmapped
+        super().stop()
+
+    def _stop_device_scheduler(self) -> None:
+        if getattr(self, "device_scheduler", None) is not None:
+            try:
+                self.device_scheduler_stats = self.device_scheduler.stop()
+                self.log(f"device scheduler (K9) stats: {self.device_scheduler_stats}")
+            except Exception as e:  # noqa: BLE001
+                self.log(f"device scheduler stop failed: {e}")
+            self.device_scheduler = None
 
     def _picklable_config(self, config):
         # the controller / searchspace objects stay on the driver; workers only need these fields
@@ -399,6 +456,7 @@ class HyperparameterOptDriver(Driver):
             r["early_stopped"] += 1
 
     def finalize(self, job_end: float) -> dict:
+        self._stop_device_scheduler()
         self.job_end = job_end
         self.duration = util.seconds_to_milliseconds(job_end - self.job_start)
         results = self.prep_results(util.time_diff(self.job_start, job_end))
@@ -442,6 +500,8 @@ class HyperparameterOptDriver(Driver):
             exp["duration"] = self.duration
             exp["config"] = json.dumps(self.result.get("best_config"), default=util.json_default_numpy)
             exp["metric"] = self.result.get("best_val")
+            if getattr(self, "device_scheduler_stats", None):
+                exp["device_scheduler"] = self.device_scheduler_stats   # K9 counters: polls / metrics / stops / mailbox
         else:
             exp["status"] = "RUNNING"
         return json.dumps(exp, default=util.json_default_numpy)

@@ -67,6 +67,9 @@ def _host():
     sig("mgr_bytes", [P], u64)
     sig("mgr_num_workers", [P], u32)
     sig("mgr_payload_bytes", [P], u32)
+    sig("mgr_set_mailbox", [P, ctypes.c_char_p, u32, u64], None)
+    sig("mgr_clear_mailbox", [P], None)
+    sig("mgr_get_mailbox", [P, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32)], u32)
     sig("mgr_now_ns", [], u64)
     sig("mgr_off_dev_ring", [P, u32], u64)
     sig("mgr_off_ctl", [P, u32], u64)
@@ -310,18 +313,32 @@ class WorkerChannel:
             u64, P = ctypes.c_ulonglong, ctypes.c_void_p
             cu.mg_ring_map.argtypes, cu.mg_ring_map.restype = [P, u64], u64
             cu.mg_report_store.argtypes = [u64, u64, u64, ctypes.c_uint, P, ctypes.c_int, ctypes.c_longlong, u64,
-                                           ctypes.c_uint, P, P]
+                                           ctypes.c_uint, P, u64, ctypes.c_uint, ctypes.c_uint, ctypes.c_longlong, P]
             cu.mg_report_store.restype = ctypes.c_int
+            cu.mg_mailbox_open.argtypes, cu.mg_mailbox_open.restype = [ctypes.c_char_p], u64
+            cu.mg_mailbox_close.argtypes, cu.mg_mailbox_close.restype = [u64], ctypes.c_int
+            cu.mg_gt_offset_ns.argtypes, cu.mg_gt_offset_ns.restype = [], ctypes.c_longlong
             base = self.lib.mgr_base(self.h)
             dev_base = cu.mg_ring_map(base, self.lib.mgr_bytes(self.h))
             if not dev_base:
                 raise RuntimeError("cudaHostRegister of the control segment failed")
+            # device mailbox: the scheduler GPU's peer-visible ring (published by the driver when K9 runs); without
+            # it, or when this GPU cannot map it, the host-mapped device ring alone carries the records
+            mailbox, mbox_slots = 0, 0
+            handle = ctypes.create_string_buffer(64)
+            slots_out = ctypes.c_uint32(0)
+            if os.environ.get("MAGGY_B200_MAILBOX", "1") != "0" and \
+                    self.lib.mgr_get_mailbox(self.h, handle, ctypes.byref(slots_out)):
+                mailbox = int(cu.mg_mailbox_open(handle.raw))
+                mbox_slots = int(slots_out.value) if mailbox else 0
             self._dev = {
                 "cu": cu, "base": dev_base,
                 "off_ring": int(self.lib.mgr_off_dev_ring(self.h, self.worker)),
                 "off_ctl": int(self.lib.mgr_off_ctl(self.h, self.worker)),
                 "slots": int(self.lib.mgr_ring_slots(self.h)),
                 "state": torch.zeros(8, dtype=torch.int32, device="cuda"),
+                "mailbox": mailbox, "mbox_slots": mbox_slots, "mbox_workers": int(self.lib.mgr_num_workers(self.h)),
+                "gt_offset": int(cu.mg_gt_offset_ns()),
             }
         return self._dev
 
@@ -336,6 +353,7 @@ class WorkerChannel:
             tensor, code = tensor.float(), 0
         rc = d["cu"].mg_report_store(d["base"], d["off_ring"], d["off_ctl"], d["slots"], tensor.data_ptr(), code,
                                      int(step), int(trial_id, 16), self.worker, d["state"].data_ptr(),
+                                     d["mailbox"], d["mbox_workers"], d["mbox_slots"], d["gt_offset"],
                                      torch.cuda.current_stream().cuda_stream)
         if rc != 0:
             raise RuntimeError(f"mg_report_store failed: {rc}")
@@ -348,6 +366,8 @@ class WorkerChannel:
 
                     torch.cuda.synchronize()
                     cu = self._dev["cu"]
+                    if self._dev.get("mailbox"):
+                        cu.mg_mailbox_close(self._dev["mailbox"])
                     cu.mg_ring_unmap.argtypes, cu.mg_ring_unmap.restype = [ctypes.c_void_p], ctypes.c_int
                     cu.mg_ring_unmap(self.lib.mgr_base(self.h))
                 except Exception:

@@ -17,7 +17,7 @@ from . import rpc
 
 class DeviceScheduler:
     def __init__(self, channel: "rpc.DriverChannel", direction: str = "max", es_min: int = 10, es_interval: int = 1,
-                 max_steps: int = 1024, cap_final: int = 1024, device="cuda:0"):
+                 max_steps: int = 1024, cap_final: int = 1024, device="cuda:0", use_mailbox: bool = True):
         self.ch = channel
         self.device = torch.device(device)
         self.direction = 1 if direction == "max" else -1
@@ -28,8 +28,15 @@ class DeviceScheduler:
         self._u64 = u64
         self.cu.mg_ring_map.argtypes, self.cu.mg_ring_map.restype = [P, u64], u64
         self.cu.mg_sched_scratch_bytes.argtypes, self.cu.mg_sched_scratch_bytes.restype = [u32, u32, u32], u64
-        self.cu.mg_sched_start.argtypes = [u64, u64, u64, u64, u64, u32, u32, i32, u32, u32, u32, u32, P, u64, P]
+        self.cu.mg_sched_start.argtypes = [u64, u64, u64, u64, u64, u32, u32, i32, u32, u32, u32, u32, P, u64, u64, u32,
+                                           ctypes.c_longlong, P]
         self.cu.mg_sched_start.restype = i32
+        self.cu.mg_mailbox_create.argtypes, self.cu.mg_mailbox_create.restype = [u32, u32, ctypes.c_char_p], u64
+        self.cu.mg_mailbox_free.argtypes, self.cu.mg_mailbox_free.restype = [u64], i32
+        self.cu.mg_gt_offset_ns.argtypes, self.cu.mg_gt_offset_ns.restype = [], ctypes.c_longlong
+        self.use_mailbox = use_mailbox
+        self.mailbox = 0
+        self.mailbox_slots = 256
         self.stream = None
         self.running = False
 
@@ -56,9 +63,19 @@ class DeviceScheduler:
             off_dev0 = int(host.mgr_off_dev_ring(h, 0))
             off_host0 = int(host.mgr_off_host_ring(h, 0))
             ring_stride = int(host.mgr_ring_stride(h))
+            self.cu.mg_set_device(self.device.index or 0)
+            if self.use_mailbox:
+                # peer-visible record rings + STOP words in THIS GPU's memory; the handle travels through the segment
+                handle = ctypes.create_string_buffer(64)
+                self.mailbox = int(self.cu.mg_mailbox_create(W, self.mailbox_slots, handle))
+                if self.mailbox:
+                    host.mgr_set_mailbox(h, handle.raw, self.mailbox_slots,
+                                         W * (64 + 64 * self.mailbox_slots))
+            self.gt_offset = int(self.cu.mg_gt_offset_ns())
             rc = self.cu.mg_sched_start(base, off_ctl, off_host0, off_dev0, ring_stride, W,
                                         int(host.mgr_ring_slots(h)), self.direction, self.es_min, self.es_interval,
                                         self.max_steps, self.cap_final, self.scratch.data_ptr(), quit_dev,
+                                        self.mailbox, self.mailbox_slots if self.mailbox else 0, self.gt_offset,
                                         self.stream.cuda_stream)
             if rc != 0:
                 raise RuntimeError(f"mg_sched_start failed: {rc}")
@@ -69,8 +86,9 @@ class DeviceScheduler:
         W = self.ch.num_workers
         off = 4 * self.cap_final * self.max_steps + 4 * self.cap_final + 8 + 4 * W * self.max_steps
         off = (off + 7) // 8 * 8 + 8 * W * 2
-        raw = self.scratch[off:off + 32].cpu().view(torch.int64).tolist()
-        return {"polls": raw[0], "metrics": raw[1], "stops": raw[2], "finals": raw[3]}
+        raw = self.scratch[off:off + 40].cpu().view(torch.int64).tolist()
+        return {"polls": raw[0], "metrics": raw[1], "stops": raw[2], "finals": raw[3], "mailbox_records": raw[4],
+                "mailbox": bool(self.mailbox)}
 
     def stop(self) -> dict:
         if self.running:
@@ -80,5 +98,10 @@ class DeviceScheduler:
             stats = self.stats()
             self.cu.mg_ring_unmap.argtypes, self.cu.mg_ring_unmap.restype = [ctypes.c_void_p], ctypes.c_int
             self.cu.mg_ring_unmap(self._host_base)  # never leave a registration behind an unmapped segment
+            if self.mailbox:
+                # workers that still hold the IPC mapping keep the allocation alive until they close it
+                self.ch.lib.mgr_clear_mailbox(self.ch.h)
+                self.cu.mg_mailbox_free(self.mailbox)
+                self.mailbox = 0
             return stats
         return self.stats()

@@ -354,6 +354,24 @@ void mgr_close(void* hv, int unlink_it) {
 void* mgr_base(void* hv) { return static_cast<Handle*>(hv)->base; }
 uint64_t mgr_bytes(void* hv) { return static_cast<Handle*>(hv)->bytes; }
 uint32_t mgr_num_workers(void* hv) { return static_cast<Handle*>(hv)->hdr()->num_workers; }
+// device mailbox handle (published by the driver once its scheduler kernel owns the allocation; read by the workers)
+void mgr_set_mailbox(void* hv, const uint8_t* handle, uint32_t slots, uint64_t bytes) {
+  MgHeader* hd = static_cast<Handle*>(hv)->hdr();
+  memcpy(hd->mailbox_handle, handle, 64);
+  hd->mailbox_slots = slots;
+  hd->mailbox_bytes = bytes;
+  __atomic_store_n(&hd->mailbox_valid, handle ? 1u : 0u, __ATOMIC_RELEASE);
+}
+void mgr_clear_mailbox(void* hv) {
+  __atomic_store_n(&static_cast<Handle*>(hv)->hdr()->mailbox_valid, 0u, __ATOMIC_RELEASE);
+}
+uint32_t mgr_get_mailbox(void* hv, uint8_t* handle_out, uint32_t* slots_out) {
+  MgHeader* hd = static_cast<Handle*>(hv)->hdr();
+  if (__atomic_load_n(&hd->mailbox_valid, __ATOMIC_ACQUIRE) == 0) return 0;
+  memcpy(handle_out, hd->mailbox_handle, 64);
+  *slots_out = hd->mailbox_slots;
+  return 1;
+}
 // size of one assign / blob slot: workers size their receive buffer from the segment, not from a constant
 uint32_t mgr_payload_bytes(void* hv) { return static_cast<Handle*>(hv)->hdr()->payload_bytes; }
 uint64_t mgr_now_ns() { return now_ns(); }

@@ -13,18 +13,33 @@
 //   the per-worker STOP word itself. It only *observes* the rings (private cursors; the host pump
 //   stays the consumer that advances `tail`), so host and device policy engines can both run — STOP is
 //   idempotent — and the decision latency is one poll iteration instead of two 1 s heartbeats.
+//
+// Device mailbox (round 2): the scheduler's GPU owns a peer-visible allocation (MgMailboxCtl + one record ring per
+// worker, mg_ring.h) that every worker maps through CUDA IPC. K8 then ALSO stores its record there — a 64-byte
+// NVLink store — and reads the STOP word from it; K9 polls its own HBM instead of host memory over PCIe and writes
+// STOP into both places. The host-mapped ring keeps receiving the same records: it is what the Python driver's
+// bookkeeping (trial.json metric history) consumes.
+//
+// Clocks: device stamps are %globaltimer + a per-process offset measured against CLOCK_MONOTONIC at start-up
+// (mg_gt_offset_ns), so every t_ns / stop_t_ns in the segment lives in ONE clock domain; K8 no longer touches the
+// worker's heartbeat word (the host heartbeat thread owns it).
 #include "../include/mg_ptx.cuh"
 #include "../include/mg_ring.h"
+
+#include <string.h>
+#include <time.h>
 
 #include <cuda_fp16.h>
 
 namespace {
 using namespace mg;
 
-struct DevProducer {  // lives in device memory, one per worker process
-  unsigned long long head;     // records produced so far on the device ring
+struct DevProducer {  // lives in device memory, one per worker process (32 zeroed bytes)
+  unsigned long long head;       // records produced so far on the host-mapped device ring
   unsigned long long dropped;
-  unsigned int last_stop;      // 1 if the last published trial had its STOP word set at publish time
+  unsigned int last_stop;        // 1 if the last published trial had its STOP word set at publish time
+  unsigned int pad;
+  unsigned long long mbox_head;  // records produced so far on the mailbox ring
 };
 
 __device__ __forceinline__ double load_metric(const void* p, int dtype) {
@@ -40,36 +55,64 @@ __global__ void report_store_kernel(uint8_t* base, unsigned long long off_ring,
                                     unsigned long long off_ctl, unsigned int slots,
                                     const void* metric, int dtype, long long step,
                                     unsigned long long trial_id, unsigned int worker,
-                                    DevProducer* st) {
+                                    DevProducer* st, uint8_t* mailbox, unsigned int mbox_workers,
+                                    unsigned int mbox_slots, long long gt_offset_ns) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   MgRing* ring = reinterpret_cast<MgRing*>(base + off_ring);
   MgRecord* sl = reinterpret_cast<MgRecord*>(base + off_ring + sizeof(MgRing));
   MgWorkerCtl* ctl = reinterpret_cast<MgWorkerCtl*>(base + off_ctl);
+  const double value = load_metric(metric, dtype);
+  const unsigned long long now = globaltimer_ns() + static_cast<unsigned long long>(gt_offset_ns);
+  bool stop = false;
+  if (mailbox) {
+    // peer-visible ring in the scheduler GPU's memory: never blocks (K9 keeps a private cursor and resynchronises
+    // when lapped), written with the same "seq last, release" protocol
+    MgMailboxCtl* mc = reinterpret_cast<MgMailboxCtl*>(mailbox) + worker;
+    MgRecord* ms = reinterpret_cast<MgRecord*>(mailbox + static_cast<size_t>(mbox_workers) * sizeof(MgMailboxCtl) +
+                                              static_cast<size_t>(worker) * mbox_slots * sizeof(MgRecord));
+    const unsigned long long mh = st->mbox_head;
+    MgRecord* s = &ms[mh & (mbox_slots - 1)];
+    s->type = MG_REC_METRIC;
+    s->worker = static_cast<uint16_t>(worker);
+    s->aux = 1;
+    s->trial_id = trial_id;
+    s->step = step;
+    s->value = value;
+    s->t_ns = now;
+    s->reserved[0] = 0;
+    s->reserved[1] = 0;
+    __threadfence_system();
+    st_release_sys_u64(&s->seq, mh + 1);
+    st->mbox_head = mh + 1;
+    st_release_sys_u64(&mc->head, mh + 1);
+    stop = ld_acquire_sys_u64(&mc->stop_trial_id) == trial_id;
+  }
   const unsigned long long head = st->head;
   const unsigned long long tail = ld_acquire_sys_u64(reinterpret_cast<const uint64_t*>(&ring->tail));
   if (head - tail >= slots) {  // consumer is behind: metrics are droppable, never block the stream
     st->dropped += 1;
     st_release_sys_u64(reinterpret_cast<uint64_t*>(&ring->dropped), st->dropped);
-    return;
+  } else {
+    MgRecord* s = &sl[head & (slots - 1)];
+    s->type = MG_REC_METRIC;
+    s->worker = static_cast<uint16_t>(worker);
+    s->aux = 1;  // produced on device
+    s->trial_id = trial_id;
+    s->step = step;
+    s->value = value;
+    s->t_ns = now;
+    s->reserved[0] = 0;
+    s->reserved[1] = 0;
+    __threadfence_system();
+    st_release_sys_u64(&s->seq, head + 1);
+    st->head = head + 1;
+    st_release_sys_u64(reinterpret_cast<uint64_t*>(&ring->head), head + 1);
   }
-  MgRecord* s = &sl[head & (slots - 1)];
-  s->type = MG_REC_METRIC;
-  s->worker = static_cast<uint16_t>(worker);
-  s->aux = 1;  // produced on device
-  s->trial_id = trial_id;
-  s->step = step;
-  s->value = load_metric(metric, dtype);
-  s->t_ns = globaltimer_ns();
-  s->reserved[0] = 0;
-  s->reserved[1] = 0;
-  __threadfence_system();
-  st_release_sys_u64(&s->seq, head + 1);
-  st->head = head + 1;
-  st_release_sys_u64(reinterpret_cast<uint64_t*>(&ring->head), head + 1);
-  st_release_sys_u64(reinterpret_cast<uint64_t*>(&ctl->heartbeat_ns), s->t_ns);
-  st->last_stop =
-      (ld_acquire_sys_u64(reinterpret_cast<const uint64_t*>(&ctl->stop_trial_id)) == trial_id) ? 1u : 0u;
+  stop = stop || ld_acquire_sys_u64(reinterpret_cast<const uint64_t*>(&ctl->stop_trial_id)) == trial_id;
+  st->last_stop = stop ? 1u : 0u;
 }
+
+__global__ void globaltimer_probe_kernel(unsigned long long* out) { *out = globaltimer_ns(); }
 
 // ---------------------------------------------------------------------------------------------------
 // K9: persistent scheduler / policy kernel
@@ -87,7 +130,10 @@ struct SchedArgs {
   float* run_tab;            // [num_workers][max_steps] prefix averages of the running trial
   unsigned long long* cursors;  // [num_workers][2]
   volatile unsigned int* quit;  // host-mapped: != 0 terminates the kernel
-  unsigned long long* stats;    // [0] polls, [1] metrics seen, [2] stops issued, [3] finals seen
+  unsigned long long* stats;    // [0] polls, [1] metrics seen, [2] stops issued, [3] finals seen, [4] mailbox records
+  uint8_t* mailbox;             // device mailbox (local HBM) or nullptr
+  unsigned int mbox_slots;
+  long long gt_offset_ns;
 };
 
 struct RunState {
@@ -137,9 +183,16 @@ sched_kernel(const SchedArgs a) {
       for (int which = 0; which < 2; ++which) {
         const unsigned long long off = (which ? a.off_dev_ring : a.off_host_ring) + w * a.ring_stride;
         MgRecord* sl = reinterpret_cast<MgRecord*>(a.base + off + sizeof(MgRing));
+        unsigned int slots = a.slots;
+        if (which == 1 && a.mailbox) {
+          // device-produced records are read from the mailbox in this GPU's own memory, not from the host mapping
+          sl = reinterpret_cast<MgRecord*>(a.mailbox + static_cast<size_t>(a.num_workers) * sizeof(MgMailboxCtl) +
+                                           static_cast<size_t>(w) * a.mbox_slots * sizeof(MgRecord));
+          slots = a.mbox_slots;
+        }
         unsigned long long cur = a.cursors[w * 2 + which];
         for (int burst = 0; burst < 64; ++burst) {
-          MgRecord* s = &sl[cur & (a.slots - 1)];
+          MgRecord* s = &sl[cur & (slots - 1)];
           const unsigned long long seq = ld_acquire_sys_u64(&s->seq);
           if (seq < cur + 1) break;                        // nothing new
           if (seq > cur + 1) { cur = seq - 1; }            // we were lapped: resynchronise
@@ -148,6 +201,7 @@ sched_kernel(const SchedArgs a) {
           const long long step = s->step;
           const double value = s->value;
           ++cur;
+          if (which == 1 && a.mailbox) atomicAdd(&a.stats[4], 1ull);
           if (type == MG_REC_METRIC) {
             if (rs.trial_id != tid) {
               rs.trial_id = tid; rs.last_step = LLONG_MIN; rs.n = 0; rs.sum = 0; rs.stopped = false;
@@ -171,7 +225,14 @@ sched_kernel(const SchedArgs a) {
                   const bool stop = a.direction >= 0 ? (rs.best < med) : (rs.best > med);
                   if (stop) {
                     rs.stopped = true;
-                    ctl->stop_t_ns = globaltimer_ns();
+                    const unsigned long long t_stop = globaltimer_ns() + static_cast<unsigned long long>(a.gt_offset_ns);
+                    if (a.mailbox) {
+                      MgMailboxCtl* mc = reinterpret_cast<MgMailboxCtl*>(a.mailbox) + w;
+                      mc->stop_t_ns = t_stop;
+                      st_release_sys_u64(&mc->stop_trial_id, tid);   // the worker's K8 reads this word over NVLink
+                      red_release_sys_add_u32(&mc->stop_seq, 1u);
+                    }
+                    ctl->stop_t_ns = t_stop;
                     st_release_sys_u64(reinterpret_cast<uint64_t*>(&ctl->stop_trial_id), tid);
                     red_release_sys_add_u32(&ctl->stop_seq, 1u);
                     atomicAdd(&a.stats[2], 1ull);
@@ -235,21 +296,71 @@ int mg_ring_unmap(void* host_base) {
   return cudaHostUnregister(host_base) == cudaSuccess ? 0 : -1;
 }
 
-// dtype: 0 fp32, 1 bf16, 2 fp16, 3 fp64. `producer_state` = 32 zeroed bytes of device memory.
+// CLOCK_MONOTONIC - %globaltimer of the current device, in ns (median of 5 probes): added to every device stamp
+long long mg_gt_offset_ns() {
+  unsigned long long* pinned = nullptr;
+  if (cudaHostAlloc(&pinned, sizeof(*pinned), cudaHostAllocMapped) != cudaSuccess) return 0;
+  long long best[5];
+  for (int i = 0; i < 5; ++i) {
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    globaltimer_probe_kernel<<<1, 1>>>(pinned);
+    cudaDeviceSynchronize();
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const long long m0 = t0.tv_sec * 1000000000ll + t0.tv_nsec, m1 = t1.tv_sec * 1000000000ll + t1.tv_nsec;
+    best[i] = (m0 + m1) / 2 - static_cast<long long>(*pinned);
+  }
+  cudaFreeHost(pinned);
+  for (int i = 0; i < 5; ++i)
+    for (int j = i + 1; j < 5; ++j)
+      if (best[j] < best[i]) { long long t = best[i]; best[i] = best[j]; best[j] = t; }
+  return best[2];
+}
+
+// ---- device mailbox -------------------------------------------------------------------------------------------
+// create (driver process, on the scheduler's GPU): zeroed allocation + its CUDA IPC handle (64 bytes)
+unsigned long long mg_mailbox_create(unsigned int num_workers, unsigned int slots, unsigned char* handle_out) {
+  void* p = nullptr;
+  const size_t bytes = mg_mailbox_bytes(num_workers, slots);
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cudaMemset(p, 0, bytes);
+  cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return 0; }
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &h, 64);
+  return reinterpret_cast<unsigned long long>(p);
+}
+int mg_mailbox_free(unsigned long long p) { return cudaFree(reinterpret_cast<void*>(p)) == cudaSuccess ? 0 : -1; }
+// open (worker process): peer mapping of the scheduler GPU's allocation into this process; 0 if P2P is not possible
+unsigned long long mg_mailbox_open(const unsigned char* handle) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void* p = nullptr;
+  if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return reinterpret_cast<unsigned long long>(p);
+}
+int mg_mailbox_close(unsigned long long p) {
+  return cudaIpcCloseMemHandle(reinterpret_cast<void*>(p)) == cudaSuccess ? 0 : -1;
+}
+
+// dtype: 0 fp32, 1 bf16, 2 fp16, 3 fp64. `producer_state` = 32 zeroed bytes of device memory. `mailbox` may be 0.
 int mg_report_store(unsigned long long dev_base, unsigned long long off_ring,
                     unsigned long long off_ctl, unsigned int slots, const void* metric, int dtype,
                     long long step, unsigned long long trial_id, unsigned int worker,
-                    void* producer_state, void* stream) {
+                    void* producer_state, unsigned long long mailbox, unsigned int mbox_workers,
+                    unsigned int mbox_slots, long long gt_offset_ns, void* stream) {
   report_store_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<uint8_t*>(dev_base), off_ring, off_ctl, slots, metric, dtype, step, trial_id,
-      worker, reinterpret_cast<DevProducer*>(producer_state));
+      worker, reinterpret_cast<DevProducer*>(producer_state), reinterpret_cast<uint8_t*>(mailbox), mbox_workers,
+      mbox_slots, gt_offset_ns);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
 }
 
 // scratch layout (device memory, zeroed by the caller), in this order:
 //   float  final_tab[cap_final*max_steps]; uint final_len[cap_final]; uint num_final[2];
-//   float  run_tab[num_workers*max_steps]; u64 cursors[num_workers*2]; u64 stats[4]
+//   float  run_tab[num_workers*max_steps]; u64 cursors[num_workers*2]; u64 stats[8]
 unsigned long long mg_sched_scratch_bytes(unsigned int num_workers, unsigned int max_steps,
                                           unsigned int cap_final) {
   unsigned long long b = 0;
@@ -259,7 +370,7 @@ unsigned long long mg_sched_scratch_bytes(unsigned int num_workers, unsigned int
   b += 4ull * num_workers * max_steps;
   b = (b + 7) / 8 * 8;
   b += 8ull * num_workers * 2;
-  b += 8ull * 4;
+  b += 8ull * 8;
   return b;
 }
 
@@ -268,7 +379,8 @@ int mg_sched_start(unsigned long long dev_base, unsigned long long off_ctl,
                    unsigned long long ring_stride, unsigned int num_workers, unsigned int slots,
                    int direction, unsigned int es_min, unsigned int es_interval,
                    unsigned int max_steps, unsigned int cap_final, void* scratch,
-                   unsigned long long quit_dev_ptr, void* stream) {
+                   unsigned long long quit_dev_ptr, unsigned long long mailbox, unsigned int mbox_slots,
+                   long long gt_offset_ns, void* stream) {
   if (num_workers > 32) return -1;
   SchedArgs a;
   a.base = reinterpret_cast<uint8_t*>(dev_base);
@@ -285,6 +397,9 @@ int mg_sched_start(unsigned long long dev_base, unsigned long long off_ctl,
   a.cursors = reinterpret_cast<unsigned long long*>(p); p += 8ull * num_workers * 2;
   a.stats = reinterpret_cast<unsigned long long*>(p);
   a.quit = reinterpret_cast<volatile unsigned int*>(quit_dev_ptr);
+  a.mailbox = reinterpret_cast<uint8_t*>(mailbox);
+  a.mbox_slots = mbox_slots;
+  a.gt_offset_ns = gt_offset_ns;
   sched_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);

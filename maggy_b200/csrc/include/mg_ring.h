@@ -18,7 +18,7 @@
 #include <stdint.h>
 
 #define MG_RING_MAGIC 0x4d47523162323030ull /* "MGR1b200" */
-#define MG_RING_VERSION 2u
+#define MG_RING_VERSION 3u
 
 enum MgRecType : uint16_t {
   MG_REC_NONE = 0,
@@ -113,7 +113,32 @@ struct alignas(64) MgHeader {
   alignas(64) uint32_t doorbell;   // bumped + futex-woken by host producers
   uint32_t gstop;                  // global stop
   uint32_t driver_alive;
+  // ---- device mailbox (GPU memory owned by the driver process, reached by the workers' GPUs over NVLink)
+  alignas(64) uint32_t mailbox_valid;   // 1 once the driver published the handle below
+  uint32_t mailbox_slots;               // records per worker ring (power of two)
+  uint64_t mailbox_bytes;
+  uint8_t mailbox_handle[64];           // cudaIpcMemHandle_t of the allocation
 };
+
+// Device mailbox: the peer-visible half of the control plane. It lives in the HBM of the GPU that runs the
+// persistent scheduler kernel (K9); every worker maps it through CUDA IPC, so `reporter.broadcast(tensor)` is a
+// 64-byte store over NVLink into this ring and K9 polls its own local memory instead of host memory across PCIe.
+struct alignas(64) MgMailboxCtl {
+  uint64_t head;            // records produced by the worker's K8 so far
+  uint64_t stop_trial_id;   // written by K9: the trial with this id must stop (mirrors MgWorkerCtl.stop_trial_id)
+  uint32_t stop_seq;
+  uint32_t pad;
+  uint64_t stop_t_ns;
+  uint64_t reserved[3];
+};
+
+static inline uint64_t mg_mailbox_bytes(uint32_t num_workers, uint32_t slots) {
+  return (uint64_t)num_workers * (sizeof(MgMailboxCtl) + (uint64_t)slots * sizeof(MgRecord));
+}
+// byte offset of worker w's ring inside the mailbox (the MgMailboxCtl array comes first)
+static inline uint64_t mg_mailbox_ring_off(uint32_t num_workers, uint32_t slots, uint32_t w) {
+  return (uint64_t)num_workers * sizeof(MgMailboxCtl) + (uint64_t)w * slots * sizeof(MgRecord);
+}
 
 static inline uint64_t mg_ring_bytes(uint32_t slots) {
   return sizeof(MgRing) + (uint64_t)slots * sizeof(MgRecord);

@@ -50,3 +50,45 @@ def test_hpo_on_gpu_workers(tmp_path, monkeypatch):
     assert trial["step_history"] == list(range(12))               # every device-side report reached the driver
     assert trial["metric_history"][-1] == pytest.approx(res["best_val"], abs=0.05)
     assert trial["metric_history"][-1] > trial["metric_history"][0]
+
+
+def train_constant_quality_on_device(hparams, reporter):
+    import time
+
+    import torch
+
+    q = torch.tensor(float(hparams["q"]), device="cuda")
+    for step in range(80):
+        reporter.broadcast(q, step)          # a CUDA tensor: published by K8 (mailbox + host-mapped ring)
+        time.sleep(0.002)
+    return float(hparams["q"])
+
+
+def test_device_scheduler_stops_trials_during_a_real_lagom_run(tmp_path, monkeypatch):
+    """K9 is started by HyperparameterOptDriver.init and is the ONLY native policy engine here (host engine off):
+    the STOP words that end the bad trials early were written by the persistent kernel."""
+    from maggy_b200 import Searchspace, experiment
+    from maggy_b200.config import HyperparameterOptConfig
+    from maggy_b200.core.environment.singleton import EnvSing
+
+    monkeypatch.setenv("MAGGY_LOG_DIR", str(tmp_path / "experiment_log"))
+    monkeypatch.setenv("MAGGY_NUM_EXECUTORS", "1")
+    monkeypatch.setenv("MAGGY_B200_DEVICE_SCHED", "1")
+    monkeypatch.setenv("MAGGY_B200_HOST_POLICY", "0")
+    EnvSing.reset()
+    sp = Searchspace(q=("DOUBLE", [0.0, 1.0]))
+    cfg = HyperparameterOptConfig(num_trials=10, optimizer="randomsearch", searchspace=sp, direction="max",
+                                  es_policy="median", es_interval=1, es_min=2, name="gpu_k9", seed=3)
+    res = experiment.lagom(train_constant_quality_on_device, cfg)
+    EnvSing.reset()
+    root = str(tmp_path / "experiment_log")
+    run = os.path.join(root, os.listdir(root)[0], "1")
+    meta = json.load(open(os.path.join(run, "maggy.json")))
+    k9 = meta["device_scheduler"]
+    assert res["num_trials"] == 10
+    assert k9["stops"] >= 1 and k9["metrics"] > 50 and k9["finals"] >= 3, k9
+    assert res["early_stopped"] >= 1
+    stopped = [json.load(open(os.path.join(run, t, "trial.json"))) for t in os.listdir(run)
+               if os.path.exists(os.path.join(run, t, "trial.json"))]
+    short = [t for t in stopped if t["early_stop"]]
+    assert short and all(len(t["metric_history"]) < 80 for t in short)
