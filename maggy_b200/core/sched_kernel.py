@@ -7,6 +7,7 @@ and returns the kernel's counters. The Python driver keeps consuming the same re
 """
 from __future__ import annotations
 
+import atexit
 import ctypes
 
 import torch
@@ -80,12 +81,23 @@ class DeviceScheduler:
             if rc != 0:
                 raise RuntimeError(f"mg_sched_start failed: {rc}")
         self.running = True
+        # a persistent kernel that outlives its owner keeps the CUDA context (and the process) from shutting down
+        atexit.register(self._raise_quit)
         return self
+
+    def _raise_quit(self):
+        try:
+            self.quit[0] = 1
+        except Exception:  # noqa: BLE001
+            pass
+
+    def __del__(self):
+        self._raise_quit()
 
     def stats(self) -> dict:
         W = self.ch.num_workers
         off = 4 * self.cap_final * self.max_steps + 4 * self.cap_final + 8 + 4 * W * self.max_steps
-        off = (off + 7) // 8 * 8 + 8 * W * 2
+        off = (off + 7) // 8 * 8 + 8 * W * 3
         raw = self.scratch[off:off + 40].cpu().view(torch.int64).tolist()
         return {"polls": raw[0], "metrics": raw[1], "stops": raw[2], "finals": raw[3], "mailbox_records": raw[4],
                 "mailbox": bool(self.mailbox)}

@@ -128,7 +128,7 @@ struct SchedArgs {
   unsigned int* final_len;   // [cap_final]
   unsigned int* num_final;   // [1]
   float* run_tab;            // [num_workers][max_steps] prefix averages of the running trial
-  unsigned long long* cursors;  // [num_workers][2]
+  unsigned long long* cursors;  // [num_workers][3]: host ring, host-mapped device ring, mailbox ring
   volatile unsigned int* quit;  // host-mapped: != 0 terminates the kernel
   unsigned long long* stats;    // [0] polls, [1] metrics seen, [2] stops issued, [3] finals seen, [4] mailbox records
   uint8_t* mailbox;             // device mailbox (local HBM) or nullptr
@@ -180,17 +180,23 @@ sched_kernel(const SchedArgs a) {
   unsigned long long polls = 0;
   while (*a.quit == 0) {
     if (active) {
-      for (int which = 0; which < 2; ++which) {
+      for (int which = 0; which < 3; ++which) {
         const unsigned long long off = (which ? a.off_dev_ring : a.off_host_ring) + w * a.ring_stride;
         MgRecord* sl = reinterpret_cast<MgRecord*>(a.base + off + sizeof(MgRing));
         unsigned int slots = a.slots;
-        if (which == 1 && a.mailbox) {
-          // device-produced records are read from the mailbox in this GPU's own memory, not from the host mapping
+        // A worker whose GPU mapped the mailbox stores every device record there (and K9 reads it from its own
+        // HBM); one that could not (no P2P, or it attached before the handle was published) only fills the
+        // host-mapped device ring. Exactly one of the two is consumed per worker.
+        const bool uses_mailbox =
+            a.mailbox && ld_acquire_sys_u64(&(reinterpret_cast<MgMailboxCtl*>(a.mailbox) + w)->head) > 0;
+        if (which == 1 && uses_mailbox) continue;
+        if (which == 2) {
+          if (!uses_mailbox) continue;
           sl = reinterpret_cast<MgRecord*>(a.mailbox + static_cast<size_t>(a.num_workers) * sizeof(MgMailboxCtl) +
                                            static_cast<size_t>(w) * a.mbox_slots * sizeof(MgRecord));
           slots = a.mbox_slots;
         }
-        unsigned long long cur = a.cursors[w * 2 + which];
+        unsigned long long cur = a.cursors[w * 3 + which];
         for (int burst = 0; burst < 64; ++burst) {
           MgRecord* s = &sl[cur & (slots - 1)];
           const unsigned long long seq = ld_acquire_sys_u64(&s->seq);
@@ -201,7 +207,7 @@ sched_kernel(const SchedArgs a) {
           const long long step = s->step;
           const double value = s->value;
           ++cur;
-          if (which == 1 && a.mailbox) atomicAdd(&a.stats[4], 1ull);
+          if (which == 2) atomicAdd(&a.stats[4], 1ull);
           if (type == MG_REC_METRIC) {
             if (rs.trial_id != tid) {
               rs.trial_id = tid; rs.last_step = LLONG_MIN; rs.n = 0; rs.sum = 0; rs.stopped = false;
@@ -257,7 +263,7 @@ sched_kernel(const SchedArgs a) {
             atomicAdd(&a.stats[3], 1ull);
           }
         }
-        a.cursors[w * 2 + which] = cur;
+        a.cursors[w * 3 + which] = cur;
       }
     }
     ++polls;
@@ -360,7 +366,7 @@ int mg_report_store(unsigned long long dev_base, unsigned long long off_ring,
 
 // scratch layout (device memory, zeroed by the caller), in this order:
 //   float  final_tab[cap_final*max_steps]; uint final_len[cap_final]; uint num_final[2];
-//   float  run_tab[num_workers*max_steps]; u64 cursors[num_workers*2]; u64 stats[8]
+//   float  run_tab[num_workers*max_steps]; u64 cursors[num_workers*3]; u64 stats[8]
 unsigned long long mg_sched_scratch_bytes(unsigned int num_workers, unsigned int max_steps,
                                           unsigned int cap_final) {
   unsigned long long b = 0;
@@ -369,7 +375,7 @@ unsigned long long mg_sched_scratch_bytes(unsigned int num_workers, unsigned int
   b += 8;
   b += 4ull * num_workers * max_steps;
   b = (b + 7) / 8 * 8;
-  b += 8ull * num_workers * 2;
+  b += 8ull * num_workers * 3;
   b += 8ull * 8;
   return b;
 }
@@ -394,7 +400,7 @@ int mg_sched_start(unsigned long long dev_base, unsigned long long off_ctl,
   a.num_final = reinterpret_cast<unsigned int*>(p); p += 8;
   a.run_tab = reinterpret_cast<float*>(p); p += 4ull * num_workers * max_steps;
   p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 7) / 8 * 8);
-  a.cursors = reinterpret_cast<unsigned long long*>(p); p += 8ull * num_workers * 2;
+  a.cursors = reinterpret_cast<unsigned long long*>(p); p += 8ull * num_workers * 3;
   a.stats = reinterpret_cast<unsigned long long*>(p);
   a.quit = reinterpret_cast<volatile unsigned int*>(quit_dev_ptr);
   a.mailbox = reinterpret_cast<uint8_t*>(mailbox);

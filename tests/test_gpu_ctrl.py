@@ -79,22 +79,24 @@ def test_persistent_scheduler_kernel_applies_median_rule():
     torch.cuda.synchronize()
     sched = DeviceScheduler(d, direction="max", es_min=0, es_interval=1, max_steps=32, cap_final=64)
     sched.start()
-    good = Trial({"g": 1})
-    for s in range(4):
-        w0.post_metric(good.trial_id, 0.9, s)
-    w0.post_final(good.trial_id, 0.9)
-    time.sleep(0.2)
-    bad = Trial({"b": 1})
-    t_post = time.perf_counter()
-    w1.post_metric_device(bad.trial_id, bad_metric, 0)
-    while not w1.check_stop(bad.trial_id):
-        assert time.perf_counter() - t_post < 5.0, sched.stats()
-    latency_ms = (time.perf_counter() - t_post) * 1e3
-    ok = Trial({"ok": 1})
-    w0.post_metric(ok.trial_id, 0.95, 0)
-    time.sleep(0.2)
-    assert not w0.check_stop(ok.trial_id)
-    stats = sched.stop()
+    try:   # a persistent kernel left running keeps the process from exiting: always stop it
+        good = Trial({"g": 1})
+        for s in range(4):
+            w0.post_metric(good.trial_id, 0.9, s)
+        w0.post_final(good.trial_id, 0.9)
+        time.sleep(0.2)
+        bad = Trial({"b": 1})
+        t_post = time.perf_counter()
+        w1.post_metric_device(bad.trial_id, bad_metric, 0)
+        while not w1.check_stop(bad.trial_id):
+            assert time.perf_counter() - t_post < 5.0, sched.stats()
+        latency_ms = (time.perf_counter() - t_post) * 1e3
+        ok = Trial({"ok": 1})
+        w0.post_metric(ok.trial_id, 0.95, 0)
+        time.sleep(0.2)
+        assert not w0.check_stop(ok.trial_id)
+    finally:
+        stats = sched.stop()
     assert stats["stops"] == 1 and stats["metrics"] >= 6 and stats["finals"] == 1 and stats["polls"] > 10
     assert latency_ms < 100.0
     for c in (w0, w1):
