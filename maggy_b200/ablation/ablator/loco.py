@@ -13,6 +13,7 @@ from the Hopsworks feature store:
 from __future__ import annotations
 
 import functools
+import os
 import inspect
 
 from ...core.exceptions import BadArgumentsError, NotSupportedError
@@ -71,7 +72,12 @@ class LOCO(AbstractAblator):
                 + len(s.model.layers.included_groups) + len(s.model.custom_model_generators) + 1)
 
     # ------------------------------------------------------------------ generators
-    def get_dataset_generator(self, ablated_feature=None, dataset_type="custom", shuffle_buffer_size=10000):
+    def get_dataset_generator(self, ablated_feature=None, dataset_type="store", shuffle_buffer_size=10000):
+        """Dataset factory of one trial. A user-supplied generator wins (it receives ``ablated_feature`` if it takes
+        that argument); otherwise the study's training dataset is read from the feature store with the ablated
+        feature's column left out (reference :41-80 builds a TFRecord reader through hsfs; here the result is a torch
+        ``DataLoader`` over the materialised training dataset — parquet / csv files, or hsfs when it is importable).
+        The returned callable has the reference's signature ``create_dataset(num_epochs, batch_size)``."""
         gen = self.ablation_study.custom_dataset_generator
         if gen:
             try:
@@ -79,10 +85,23 @@ class LOCO(AbstractAblator):
             except (TypeError, ValueError):
                 accepts = False
             return functools.partial(gen, ablated_feature=ablated_feature) if accepts else gen
-        raise NotSupportedError(
-            "dataset type", dataset_type,
-            " Reading training datasets from the Hopsworks feature store is not available outside Hopsworks: "
-            "pass AblationStudy(..., dataset_generator=fn) or call study.set_dataset_generator(fn).")
+        if dataset_type not in ("store", "tfrecord", "parquet", "csv"):
+            raise NotSupportedError("dataset type", dataset_type,
+                                    " Use 'store' / 'parquet' / 'csv' or write your own custom dataset generator.")
+        name = self.ablation_study.hops_training_dataset_name
+        version = self.ablation_study.hops_training_dataset_version
+        label = self.ablation_study.label_name
+        if not name:
+            raise NotSupportedError(
+                "dataset type", dataset_type,
+                " The study names no training dataset: pass AblationStudy(training_dataset_name, version, label) or a "
+                "dataset_generator.")
+
+        def create_dataset(num_epochs=1, batch_size=32, shuffle=True, seed=0):
+            return feature_store_loader(name, version, label, ablated_feature, num_epochs, batch_size, shuffle,
+                                        shuffle_buffer_size, seed)
+
+        return create_dataset
 
     def get_model_generator(self, layer_identifier=None, custom_model_generator=None):
         if layer_identifier is not None and custom_model_generator is not None:
@@ -143,3 +162,72 @@ class LOCO(AbstractAblator):
 
     def finalize_experiment(self, trials):
         return
+
+
+def _read_training_dataset(name, version):
+    """The materialised training dataset as a pandas DataFrame: hsfs when importable, else the parquet / csv files
+    under the environment's training-dataset path (``EnvSing.get_training_dataset_path``)."""
+    import pandas as pd
+
+    from ...core.environment.singleton import EnvSing
+
+    env = EnvSing.get_instance()
+    try:
+        conn = env.connect_hsfs()
+        if conn is not None:
+            return conn.get_feature_store().get_training_dataset(name, version).read()
+    except Exception:  # noqa: BLE001 - fall through to the files
+        pass
+    path = env.get_training_dataset_path(name, training_dataset_version=version)
+    if not path:
+        path = os.path.join(os.environ.get("MAGGY_TRAINING_DATASETS", os.path.join(os.getcwd(), "Training_Datasets")),
+                            f"{name}_{version}")
+    if os.path.isdir(path):
+        files = sorted(os.path.join(dp, f) for dp, _, fs in os.walk(path) for f in fs
+                       if f.endswith((".parquet", ".csv")) and not f.startswith(("_", ".")))
+    else:
+        files = [p for p in (path, path + ".parquet", path + ".csv") if os.path.isfile(p)][:1]
+    if not files:
+        raise FileNotFoundError(f"training dataset {name}_{version}: no parquet / csv files under {path}")
+    frames = [pd.read_parquet(f) if f.endswith(".parquet") else pd.read_csv(f) for f in files]
+    return pd.concat(frames, ignore_index=True) if len(frames) > 1 else frames[0]
+
+
+def feature_store_loader(name, version, label, ablated_feature, num_epochs, batch_size, shuffle=True,
+                         shuffle_buffer_size=10000, seed=0):
+    """Batches ``(features[float32, B x F], label[B])`` of the training dataset without ``ablated_feature``, for
+    ``num_epochs`` epochs; pinned when a GPU is present so that the H2D copy of each batch can be asynchronous."""
+    import numpy as np
+    import torch
+
+    df = _read_training_dataset(name, version)
+    if label not in df.columns:
+        raise KeyError(f"label column {label!r} is not in training dataset {name}_{version}: {list(df.columns)}")
+    features = [c for c in df.columns if c != label]
+    if ablated_feature is not None:
+        if ablated_feature not in features:
+            raise KeyError(f"feature {ablated_feature!r} is not in training dataset {name}_{version}")
+        features.remove(ablated_feature)
+    x = torch.from_numpy(np.ascontiguousarray(df[features].to_numpy(dtype=np.float32)))
+    y_np = df[label].to_numpy()
+    y = torch.from_numpy(np.ascontiguousarray(y_np.astype(np.int64 if np.issubdtype(y_np.dtype, np.integer)
+                                                          else np.float32)))
+    if torch.cuda.is_available():
+        x, y = x.pin_memory(), y.pin_memory()
+    n = x.shape[0]
+    gen = torch.Generator().manual_seed(seed)
+
+    class _Loader:
+        feature_names = features
+
+        def __len__(self):
+            return num_epochs * ((n + batch_size - 1) // batch_size)
+
+        def __iter__(self):
+            for _ in range(num_epochs):
+                order = torch.randperm(n, generator=gen) if shuffle else torch.arange(n)
+                for i in range(0, n, batch_size):
+                    idx = order[i:i + batch_size]
+                    yield x[idx], y[idx]
+
+    return _Loader()

@@ -133,6 +133,33 @@ class Driver(ABC):
         self.channel = rpc.DriverChannel(self.num_executors, ring_slots=1024, payload_bytes=4 << 20)
         self._digest_thread = threading.Thread(target=self._digest_loop, name="maggy-digest", daemon=True)
         self._digest_thread.start()
+        self._start_log_server()
+
+    def _start_log_server(self) -> None:
+        """External LOG endpoint (reference rpc.py:490-502): on request (MAGGY_LOG_SERVER=1 | host:port) or whenever
+        the environment wants to announce the driver (Hopsworks registers it over REST for its Jupyter front-end)."""
+        self.log_server = None
+        want = os.environ.get("MAGGY_LOG_SERVER", "")
+        env = EnvSing.get_instance()
+        announce = getattr(env, "announce_driver", None)
+        if not want and announce is None:
+            return
+        try:
+            from ..logserver import LogServer
+
+            host, port = "127.0.0.1", 0
+            if ":" in want:
+                host, port = want.rsplit(":", 1)[0], int(want.rsplit(":", 1)[1])
+            elif announce is not None:
+                host = ""
+            self.log_server = LogServer(self, host, port, secret=getattr(self, "_secret", None)).start()
+            self._secret = self.log_server.secret
+            self.log(f"LOG endpoint listening on {self.log_server.address[0] or '0.0.0.0'}:{self.log_server.address[1]} "
+                     f"secret {self._secret}")
+            if announce is not None:
+                announce(self.log_server.address[1], self._secret, self.app_id, self)
+        except Exception as e:  # noqa: BLE001 - observability must never fail the experiment
+            self.log(f"LOG endpoint not started: {e}")
 
     def _launch_workers(self, train_fn, config):
         spec = self._worker_spec(train_fn, config)
@@ -244,6 +271,9 @@ class Driver(ABC):
                 self.pool.shutdown(grace_s=1.0)
         finally:
             self.pool = None
+        if getattr(self, "log_server", None) is not None:
+            self.log_server.stop()
+            self.log_server = None
         if self.channel is not None:
             try:
                 self._send_gstop()

@@ -144,5 +144,5 @@ class BaseEnv:
     def get_featurestore_metadata(self, featurestore=None, update_cache=False):
         pass
 
-    def connect_hsfs(self):
-        pass
+    def connect_hsfs(self, engine="training"):
+        return None

@@ -59,6 +59,10 @@ def main(argv=None) -> int:
             from .torch_dist_executor import torch_dist_executor_loop
 
             torch_dist_executor_loop(spec, channel, args.worker_id, args.attempt)
+        elif kind == "tf_dist":
+            from .tf_dist_executor import tf_dist_executor_loop
+
+            tf_dist_executor_loop(spec, channel, args.worker_id, args.attempt)
         elif kind == "base":
             from .base_executor import base_executor_loop
 

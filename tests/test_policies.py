@@ -310,3 +310,40 @@ def test_median_rule_matches_reference():
                 assert mine == theirs
     assert NoStoppingRule.earlystop_check(finals[0], finals, "max") is None
     assert MedianStoppingRule.earlystop_check(_mk_trial([]), finals, "max") is None
+
+
+def test_loco_feature_store_dataset_generator_drops_the_ablated_feature(tmp_path, monkeypatch):
+    """Without a custom generator LOCO reads the study's training dataset (parquet here) and leaves the ablated
+    feature's column out (reference loco.py:41-80 does it through hsfs / TFRecords)."""
+    import numpy as np
+    import pandas as pd
+
+    from maggy_b200.ablation import AblationStudy
+    from maggy_b200.ablation.ablator.loco import LOCO
+    from maggy_b200.core.environment.singleton import EnvSing
+
+    root = tmp_path / "Training_Datasets" / "titanic_2"
+    root.mkdir(parents=True)
+    rng = np.random.default_rng(0)
+    df = pd.DataFrame({"age": rng.random(10), "fare": rng.random(10), "sex": rng.integers(0, 2, 10).astype(float),
+                       "survived": rng.integers(0, 2, 10)})
+    df.iloc[:6].to_parquet(root / "part-0.parquet")
+    df.iloc[6:].to_parquet(root / "part-1.parquet")
+    monkeypatch.setenv("MAGGY_TRAINING_DATASETS", str(tmp_path / "Training_Datasets"))
+    monkeypatch.setenv("MAGGY_LOG_DIR", str(tmp_path / "log"))
+    EnvSing.reset()
+    study = AblationStudy("titanic", 2, "survived")
+    study.features.include("fare")
+    study.model.set_base_model_generator(lambda: None)
+    loco = LOCO(study, None)
+    full = loco.get_dataset_generator()(num_epochs=1, batch_size=4, shuffle=False)
+    assert full.feature_names == ["age", "fare", "sex"] and len(full) == 3
+    ablated = loco.get_dataset_generator(ablated_feature="fare")(num_epochs=2, batch_size=4, shuffle=False)
+    batches = list(ablated)
+    assert ablated.feature_names == ["age", "sex"] and len(batches) == 6
+    x0, y0 = batches[0]
+    assert tuple(x0.shape) == (4, 2) and tuple(y0.shape) == (4,) and str(y0.dtype) == "torch.int64"
+    np.testing.assert_allclose(x0.numpy(), df[["age", "sex"]].to_numpy(dtype=np.float32)[:4])
+    with pytest.raises(KeyError):
+        loco.get_dataset_generator(ablated_feature="nope")(1, 4)
+    EnvSing.reset()
