@@ -408,6 +408,9 @@ class HyperparameterOptDriver(Driver):
             return
         if data.get("logs"):
             self.add_executor_logs(data["logs"])
+        if data.get("early_stop") and not trial.get_early_stop():
+            # the STOP word was written by an engine the digest thread did not hear from (the device scheduler K9)
+            trial.set_early_stop()
         with self._controller_lock, self._store_lock:
             trial.status = Trial.FINALIZED
             trial.final_metric = data.get("metric", msg["value"])

@@ -106,6 +106,7 @@ def run_one_trial(spec, trial_id, params, reporter, log_dir, gang=None):
             retval = retval[spec["optimization_key"]]
     except exceptions.EarlyStopException as e:
         retval = e.metric
+        reporter.early_stopped = True   # travels with FINAL: whoever wrote the STOP word (host engine, K9, driver)
         reporter.log("Early Stopped Trial.", False)
     if gang is not None:
         retval = gang.mean(retval)
@@ -162,7 +163,9 @@ def trial_executor_loop(spec, channel, worker_id, attempt, gang=None):
                 reporter.reset()
                 raise
             _, _, logs = reporter.get_data()
-            channel.post_final(trial_id, metric, {"logs": logs, "wall_s": time.time() - t0})
+            channel.post_final(trial_id, metric, {"logs": logs, "wall_s": time.time() - t0,
+                                                  "early_stop": bool(getattr(reporter, "early_stopped", False))})
+            reporter.early_stopped = False
             reporter.reset()
             if proxy_rpc:
                 time.sleep(1.0)  # reference: the first GET after FINAL races the driver and sleeps 1 s (rpc.py:745-747)

@@ -57,6 +57,9 @@ def cuda():
         _sig(lib.mg_gemm_auto_splits, [c_int, c_int, c_int, c_int])
         _sig(lib.mg_gemm_fp8, [P, P, P, P, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_float, P, P, c_int, c_int, P])
         _sig(lib.mg_quant_e4m3, [P, P, c_ll, P, P, P])
+        _sig(lib.mg_mxfp8_sf_bytes, [c_int, c_int], ctypes.c_ulonglong)
+        _sig(lib.mg_quant_mxfp8, [P, c_ll, P, c_ll, P, c_int, c_int, P])
+        _sig(lib.mg_gemm_mxfp8, [P, P, P, P, P, P, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_int, P])
         _sig(lib.mg_attn_fwd, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P])
         _sig(lib.mg_attn_bwd, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P])
         _sig(lib.mg_set_device, [c_int])

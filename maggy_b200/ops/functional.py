@@ -395,6 +395,73 @@ def linear_fp8(x, weight, bias=None):
     return _LinearFP8.apply(x, weight, bias)
 
 
+def quantize_mxfp8(x: torch.Tensor):
+    """Block-scaled (OCP MXFP8) quantisation on the device: ``(q, sf)`` with ``q`` a ``torch.float8_e4m3fn`` tensor of
+    ``x``'s shape [rows, K] and ``sf`` the UE8M0 scale bytes — one per 32 elements along K — already in the chunked
+    layout the GEMM's tcgen05.cp consumes (csrc/ops/gemm_mxfp8.cu). ``K`` must be a multiple of 16."""
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[1] % 16 == 0
+    rows, K = x.shape
+    lib = _lib.cuda()
+    q = torch.empty((rows, K), dtype=torch.uint8, device=x.device)
+    sf = torch.empty(int(lib.mg_mxfp8_sf_bytes(rows, K)), dtype=torch.uint8, device=x.device)
+    rc = lib.mg_quant_mxfp8(x.data_ptr(), x.stride(0), q.data_ptr(), q.stride(0), sf.data_ptr(), rows, K, _stream())
+    _lib.check(rc, f"mg_quant_mxfp8(rows={rows},K={K})")
+    _count(1)
+    return q.view(torch.float8_e4m3fn), sf
+
+
+def dequantize_mxfp8(q: torch.Tensor, sf: torch.Tensor) -> torch.Tensor:
+    """fp32 values of a block-scaled operand (reference / test helper; plain PyTorch)."""
+    rows, K = q.shape
+    nkb = (K + 127) // 128
+    r = torch.arange(rows, device=q.device).view(-1, 1)
+    kb32 = (torch.arange(K, device=q.device) // 32).view(1, -1)
+    idx = ((r // 128) * nkb + kb32 // 4) * 512 + (r % 32) * 16 + ((r % 128) // 32) * 4 + kb32 % 4
+    e = sf.to(torch.int32)[idx].float() - 127.0
+    return q.float() * torch.exp2(e)
+
+
+def gemm_mxfp8(a_q, sfa, b_q, sfb, *, bias=None, out=None, sm_limit=0):
+    """``C[M,N] (bf16) = A_mx . B_mx^T (+ bias)`` on ``tcgen05.mma.kind::mxf8f6f4.block_scale``: e4m3 operands
+    (``a_q`` [M,K], ``b_q`` [N,K], K-major) with one UE8M0 scale per 32 K-elements applied by the tensor core."""
+    _need_cuda(a_q, b_q, bias, out)
+    assert a_q.element_size() == 1 and b_q.element_size() == 1 and a_q.stride(1) == 1 and b_q.stride(1) == 1
+    M, K = a_q.shape
+    N, Kb = b_q.shape
+    assert K == Kb, f"reduction mismatch {K} vs {Kb}"
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a_q.device)
+    rc = _lib.cuda().mg_gemm_mxfp8(a_q.data_ptr(), sfa.data_ptr(), b_q.data_ptr(), sfb.data_ptr(), out.data_ptr(),
+                                   _ptr(bias), M, N, K, a_q.stride(0), b_q.stride(0), out.stride(0), sm_limit, _stream())
+    _lib.check(rc, f"mg_gemm_mxfp8(M={M},N={N},K={K})")
+    _count(1)
+    return out
+
+
+class _LinearMXFP8(torch.autograd.Function):
+    """y = x W^T (+ b) with the forward GEMM in block-scaled fp8 (MXFP8: e4m3 + UE8M0 per 32 elements, quantised on
+    the device); dgrad / wgrad stay in bf16 on the saved bf16 operands."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        xq, sfx = quantize_mxfp8(x2)
+        wq, sfw = quantize_mxfp8(weight if weight.is_contiguous() else weight.contiguous())
+        y = gemm_mxfp8(xq, sfx, wq, sfw, bias=bias)
+        ctx.save_for_backward(x2, weight)
+        ctx.bias, ctx.weight_ref, ctx.xshape = bias, weight, x.shape
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    backward = _LinearFP8.backward
+
+
+def linear_mxfp8(x, weight, bias=None):
+    return _LinearMXFP8.apply(x, weight, bias)
+
+
 class _LayerNorm(torch.autograd.Function):
     """``with_residual=True`` additionally returns ``x`` itself (an alias, no kernel) as the tensor to feed into the
     residual connection around the normalised branch: both gradients then arrive in THIS backward and are summed

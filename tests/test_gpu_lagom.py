@@ -84,10 +84,12 @@ def test_device_scheduler_stops_trials_during_a_real_lagom_run(tmp_path, monkeyp
     root = str(tmp_path / "experiment_log")
     run = os.path.join(root, os.listdir(root)[0], "1")
     meta = json.load(open(os.path.join(run, "maggy.json")))
-    k9 = meta["device_scheduler"]
+    log = open(os.path.join(run, "maggy.log")).read()
+    k9 = meta.get("device_scheduler")
+    assert k9 is not None, log[-3000:]
     assert res["num_trials"] == 10
-    assert k9["stops"] >= 1 and k9["metrics"] > 50 and k9["finals"] >= 3, k9
-    assert res["early_stopped"] >= 1
+    assert k9["stops"] >= 1 and k9["metrics"] > 50 and k9["finals"] >= 3, (k9, log[-2000:])
+    assert res["early_stopped"] >= 1, (k9, log[-2000:])
     stopped = [json.load(open(os.path.join(run, t, "trial.json"))) for t in os.listdir(run)
                if os.path.exists(os.path.join(run, t, "trial.json"))]
     short = [t for t in stopped if t["early_stop"]]
