@@ -18,6 +18,7 @@
 // stages in TMEM (columns [0,256)), scale columns at [256,264).
 #include "../include/mg_ptx.cuh"
 
+#include <cuda_fp16.h>
 #include <cuda_fp8.h>
 
 #include <mutex>
@@ -299,6 +300,35 @@ __global__ void quant_mxfp8_kernel(const __nv_bfloat16* __restrict__ x, long lon
   }
 }
 
+// bf16 values of a block-scaled operand (the backward pass of the sharded fp8 linear needs the gathered weight in bf16)
+__global__ void dequant_mxfp8_kernel(const uint8_t* __restrict__ q, long long ldq, const uint8_t* __restrict__ sf,
+                                     __nv_bfloat16* __restrict__ out, long long ldo, int rows, int K, int num_k_blocks) {
+  const long long vec_per_row = K / 8;
+  const long long total = static_cast<long long>(rows) * vec_per_row;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / vec_per_row);
+    const int c0 = static_cast<int>(i - static_cast<long long>(r) * vec_per_row) * 8;
+    const int kb32 = c0 >> 5;
+    const size_t chunk = static_cast<size_t>(r >> 7) * num_k_blocks + (kb32 >> 2);
+    const int e = static_cast<int>(sf[chunk * 512 + (r & 31) * 16 + ((r & 127) >> 5) * 4 + (kb32 & 3)]) - 127;
+    const float s = exp2f(static_cast<float>(e));
+    const uint2 u = *reinterpret_cast<const uint2*>(q + static_cast<long long>(r) * ldq + c0);
+    float v[8];
+    const uint32_t w[2] = {u.x, u.y};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const __half2_raw h = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>((w[t >> 1] >> ((t & 1) * 16)) & 0xFFFF),
+                                                       __NV_E4M3);
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+      v[2 * t] = f.x * s;
+      v[2 * t + 1] = f.y * s;
+    }
+    *reinterpret_cast<uint4*>(out + static_cast<long long>(r) * ldo + c0) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -354,6 +384,20 @@ int mg_quant_mxfp8(const void* x, long long ldx, void* q, long long ldq, void* s
                                                              static_cast<uint8_t*>(q), ldq, static_cast<uint8_t*>(sf),
                                                              rows, K, (K + 127) / 128);
   e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
+}
+
+// out bf16 [rows, K] (row stride ldo) = q * 2^(sf - 127); K % 8 == 0
+int mg_dequant_mxfp8(const void* q, long long ldq, const void* sf, void* out, long long ldo, int rows, int K,
+                     void* stream) {
+  if (rows <= 0 || K <= 0) return 0;
+  if (K % 8 != 0 || ldq % 8 != 0 || ldo % 8 != 0) return -1;
+  long long blocks = (static_cast<long long>(rows) * (K / 8) + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  dequant_mxfp8_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(q), ldq, static_cast<const uint8_t*>(sf), static_cast<__nv_bfloat16*>(out), ldo, rows,
+      K, (K + 127) / 128);
+  cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
 }
 

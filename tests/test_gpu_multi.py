@@ -38,3 +38,15 @@ def test_sharded_linear_trains_like_the_unsharded_model():
            os.path.join(ROOT, "tests", "multi", "sharded_linear_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0 and "SHARDED_LINEAR_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_block_scaled_fp8_fsdp_path():
+    """K3-MX (all-gather of MXFP8 shards fused into the block-scaled GEMM), the peer-memory reduce-scatter kernel and a
+    ShardedLinearMX training step against PyTorch / NCCL oracles."""
+    import torch
+
+    n = min(torch.cuda.device_count(), 8)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29523", os.path.join(ROOT, "tests", "multi", "mx_fsdp_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0 and "MX_FSDP_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
