@@ -93,4 +93,7 @@ def test_device_scheduler_stops_trials_during_a_real_lagom_run(tmp_path, monkeyp
     stopped = [json.load(open(os.path.join(run, t, "trial.json"))) for t in os.listdir(run)
                if os.path.exists(os.path.join(run, t, "trial.json"))]
     short = [t for t in stopped if t["early_stop"]]
-    assert short and all(len(t["metric_history"]) < 80 for t in short)
+    lens = sorted(len(t["metric_history"]) for t in short)
+    assert short and lens[0] < 80, (lens, k9)     # (a STOP that lands on the very last report still counts as one)
+    # the records K9 judged came out of the device mailbox (GPU memory reached through CUDA IPC), not host memory
+    assert k9["mailbox"] and k9["mailbox_records"] > 50, k9
