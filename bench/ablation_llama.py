@@ -16,11 +16,13 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def make_fns(model_name, batch, seq, steps):
+def make_fns(model_name, batch, seq, steps, mode="dp", fp8=False):
     def base_model():
         from maggy_b200.models.llama import Llama, LlamaConfig
 
-        return Llama(LlamaConfig.named(model_name))
+        cfg = LlamaConfig.named(model_name)
+        cfg.fp8 = fp8
+        return Llama(cfg)
 
     def dataset(ablated_feature=None):
         return None  # synthetic tokens are generated on the device inside train_fn
@@ -37,7 +39,20 @@ def make_fns(model_name, batch, seq, steps):
             model = hparams["model_function"]()
         world = dist.get_world_size() if dist.is_initialized() else 1
         rank = dist.get_rank() if dist.is_initialized() else 0
-        flat = FlatParams(model, device=dev, world_size=world, rank=rank)
+        opt_sh = None
+        if mode == "fsdp-mx" and world > 1:
+            # BASELINE config 5 as specified: ZeRO-3 shards, block-scaled fp8, all-gather fused into the GEMM (K3-MX)
+            from maggy_b200.models.llama import shard_llama_mx
+            from maggy_b200.parallel.fsdp import ShardedLinearMX
+
+            shard_llama_mx(model)
+            shard_ids = {id(p) for m in model.modules() if isinstance(m, ShardedLinearMX) for p in m.parameters()}
+            flat = FlatParams(model, device=dev, world_size=world, rank=rank, include=lambda n, p: id(p) not in shard_ids)
+            flat_sh = FlatParams(model, device=dev, world_size=1, rank=0, include=lambda n, p: id(p) in shard_ids,
+                                 use_symmetric=False)
+            opt_sh = FusedAdamW(flat_sh, lr=1e-4, grad_scale=1.0)   # the reduce-scatter kernel already averaged
+        else:
+            flat = FlatParams(model, device=dev, world_size=world, rank=rank)
         opt = FusedAdamW(flat, lr=1e-4)
         vocab = model.cfg.vocab_size
         g = torch.Generator().manual_seed(rank)
@@ -50,9 +65,13 @@ def make_fns(model_name, batch, seq, steps):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             opt.zero_grad()
+            if opt_sh is not None:
+                opt_sh.zero_grad()
             loss = model(idx, tgt)
             loss.backward()
             opt.step()
+            if opt_sh is not None:
+                opt_sh.step()
             reporter.broadcast(-loss.detach(), step)
         e1.record()
         torch.cuda.synchronize()
@@ -74,6 +93,10 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--seq", type=int, default=2048)
     ap.add_argument("--layers", type=int, default=3, help="how many single-block ablations to include")
+    ap.add_argument("--mode", default="dp", choices=["dp", "fsdp-mx"],
+                    help="dp: replicated bf16 + fused reduce-scatter/Adam (K1); fsdp-mx: ZeRO-3 shards, block-scaled "
+                         "fp8, all-gather fused into the GEMM (K3-MX) — BASELINE config 5 as specified")
+    ap.add_argument("--fp8", default="", choices=["", "tensor", "mx"], help="dp mode: fp8 forward of the projections")
     args = ap.parse_args()
     import torch
 
@@ -84,7 +107,7 @@ def main():
     ngpu = torch.cuda.device_count()
     gpt = args.gpus_per_trial or max(1, ngpu)
     seq = min(args.seq, 128) if args.model == "llama-tiny" else args.seq
-    base_model, dataset, train_fn = make_fns(args.model, args.batch, seq, args.steps)
+    base_model, dataset, train_fn = make_fns(args.model, args.batch, seq, args.steps, args.mode, args.fp8 or False)
     study = AblationStudy("synthetic_tokens", 1, label_name="next_token", dataset_generator=dataset)
     study.model.set_base_model_generator(base_model)
     study.model.layers.include(*[f"blocks.{i}" for i in range(1, 1 + args.layers)])
@@ -104,7 +127,9 @@ def main():
         if os.path.exists(p):
             toks.append(json.load(open(p)).get("tokens_per_s"))
     toks = [t for t in toks if t]
-    print(json.dumps({"metric": f"LOCO ablation, {args.model} bf16, {gpt} GPUs/trial: tokens/s per trial and trials/hour",
+    kind = "mxfp8 ZeRO-3 (K3-MX)" if args.mode == "fsdp-mx" else ("bf16" if not args.fp8 else f"fp8-{args.fp8} forward")
+    print(json.dumps({"metric": f"LOCO ablation, {args.model} {kind}, {gpt} GPUs/trial: tokens/s per trial and trials/hour",
+                      "mode": args.mode,
                       "tokens_per_s_median": sorted(toks)[len(toks) // 2] if toks else None, "tokens_per_s_all": toks,
                       "trials": res["num_trials"], "trials_per_hour": res["num_trials"] / wall * 3600.0, "wall_s": wall,
                       "n_gpus": ngpu, "gpus_per_trial": gpt, "best_config": res["best_config"],

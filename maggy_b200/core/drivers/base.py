@@ -161,6 +161,13 @@ class Driver(ABC):
         except Exception as e:  # noqa: BLE001 - observability must never fail the experiment
             self.log(f"LOG endpoint not started: {e}")
 
+    def _scheduler_gpus(self):
+        """Physical GPU(s) the workers must be able to map besides their own (the device scheduler's mailbox)."""
+        sched = getattr(self, "device_scheduler", None)
+        if sched is not None and sched.mailbox:
+            return [int(sched.device.index or 0)]
+        return []
+
     def _launch_workers(self, train_fn, config):
         spec = self._worker_spec(train_fn, config)
         spec_path = os.path.join(self.log_dir, ".worker_spec.pkl")
@@ -168,7 +175,8 @@ class Driver(ABC):
             cloudpickle.dump(spec, f)
         self.pool = WorkerPool(self.num_executors, self.channel.name, spec_path, self.log_dir,
                                gpus_per_worker=self.gpus_per_worker,
-                               share_devices=getattr(self, "share_devices", False))
+                               share_devices=getattr(self, "share_devices", False),
+                               also_visible=self._scheduler_gpus())
         self.pool.start()
 
     # ------------------------------------------------------------------ supervision (main thread)

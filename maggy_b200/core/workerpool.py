@@ -52,7 +52,7 @@ def free_port() -> int:
 class WorkerPool:
     def __init__(self, num_workers: int, segment: str, spec_path: str, log_dir: str,
                  gpus_per_worker: int = 1, use_gpus: Optional[bool] = None, extra_env: Optional[Dict[str, str]] = None,
-                 share_devices: bool = False):
+                 share_devices: bool = False, also_visible: Optional[List[int]] = None):
         from .. import util
 
         self.lib = _launcher()
@@ -69,6 +69,9 @@ class WorkerPool:
         # share_devices: every worker sees ALL pool GPUs and selects its own by MAGGY_LOCAL_RANK (needed when
         # the workers form one collective job: peer-mapped symmetric memory wants distinct device indices)
         self.share_devices = share_devices
+        # GPUs every worker must additionally SEE (appended after its own, so cuda:0 stays its training device): the
+        # device-scheduler GPU, whose mailbox a worker can only map through CUDA IPC if that device is visible to it
+        self.also_visible = [int(g) for g in (also_visible or [])]
 
     def _slot(self, worker: int, rank: int) -> int:
         return worker * self.gang + rank
@@ -100,6 +103,9 @@ class WorkerPool:
                 gpus, local_rank = ",".join(str(worker * self.gang + r) for r in range(self.gang)), rank
             else:
                 gpus, local_rank = str(slot), 0
+            if self.use_gpus and not self.share_devices and self.also_visible:
+                mine = gpus.split(",")
+                gpus = ",".join(mine + [str(g) for g in self.also_visible if str(g) not in mine])
             env["MAGGY_LOCAL_RANK"] = str(local_rank)
             log = os.path.join(self.log_dir, f"worker_{worker}_{rank}.stdout.log")
             rc = self.lib.mgl_spawn(self.pool, slot, _blob(argv), _blob([f"{k}={v}" for k, v in env.items()]),

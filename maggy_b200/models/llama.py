@@ -26,13 +26,19 @@ class LlamaConfig:
     rope_theta: float = 500000.0
     norm_eps: float = 1e-5
     tie_embeddings: bool = True
-    fp8: bool = False  # forward qkv and gate-up projections in e4m3 on tcgen05 kind::f8f6f4 (bf16 backward)
+    # forward qkv and gate-up projections in fp8 (bf16 backward): True / "tensor" = e4m3 with per-tensor scales on
+    # tcgen05 kind::f8f6f4; "mx" = block-scaled MXFP8 (e4m3 + one UE8M0 scale per 32 elements) on
+    # tcgen05 kind::mxf8f6f4.block_scale
+    fp8: object = False
 
     @classmethod
     def named(cls, name: str) -> "LlamaConfig":
         table = {
             "llama3-1b": dict(),
             "llama-tiny": dict(vocab_size=1024, dim=128, n_layers=2, n_heads=4, n_kv_heads=2, ffn_dim=256, max_seq_len=128),
+            # small enough for tests, wide enough to shard over 2 or 4 ranks (rows per shard stay multiples of 128)
+            "llama-small": dict(vocab_size=4096, dim=512, n_layers=4, n_heads=8, n_kv_heads=4, ffn_dim=1024,
+                                max_seq_len=512),
         }
         return cls(**table[name])
 
@@ -71,8 +77,9 @@ class LlamaBlock(nn.Module):
         B, T, C = x.shape
         H, KV, hd = cfg.n_heads, cfg.n_kv_heads, C // cfg.n_heads
         h = F.rms_norm(x, self.attn_norm, cfg.norm_eps)
-        lin = F.linear_fp8 if cfg.fp8 else F.linear
-        qkv = lin(h, self.wqkv)
+        lin = F.linear_mxfp8 if cfg.fp8 == "mx" else (F.linear_fp8 if cfg.fp8 else F.linear)
+        sharded = getattr(self, "sharded_mx", False)   # ZeRO-3: projections are ShardedLinearMX modules (K3-MX)
+        qkv = self.wqkv_s(h) if sharded else lin(h, self.wqkv)
         q, k, v = qkv.split([H * hd, KV * hd, KV * hd], dim=-1)
         q = apply_rope(q.view(B, T, H, hd), cos, sin)
         k = apply_rope(k.view(B, T, KV, hd), cos, sin)
@@ -85,6 +92,11 @@ class LlamaBlock(nn.Module):
             y = torch.nn.functional.scaled_dot_product_attention(
                 q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True, enable_gqa=True)
             y = y.transpose(1, 2).reshape(B, T, C)
+        if sharded:
+            x = x + self.wo_s(y)
+            h = F.rms_norm(x, self.ffn_norm, cfg.norm_eps)
+            gate, up = self.w13_s(h).chunk(2, dim=-1)
+            return x + self.w2_s(torch.nn.functional.silu(gate) * up)
         x = F.linear(y, self.wo, residual=x)
         h = F.rms_norm(x, self.ffn_norm, cfg.norm_eps)
         gate, up = lin(h, self.w13).chunk(2, dim=-1)
@@ -128,3 +140,24 @@ class Llama(nn.Module):
         if targets is None:
             return logits
         return F.cross_entropy(logits, targets, v_real=cfg.vocab_size, reduction="mean_all")
+
+
+def shard_llama_mx(model: "Llama", group=None) -> int:
+    """ZeRO-3 + block-scaled fp8 for the decoder blocks (BASELINE.json config 5): every projection weight becomes a
+    :class:`maggy_b200.parallel.fsdp.ShardedLinearMX` — each rank keeps ``rows / world`` rows as a bf16 master shard, the
+    forward gathers the peers' MXFP8 images INSIDE the block-scaled GEMM kernel (K3-MX), the backward reduce-scatters
+    the weight gradient with the peer-memory kernel. Embedding / norms stay replicated. Returns the number of sharded
+    projections; call after the process group exists and the model sits on this rank's GPU."""
+    from ..parallel.fsdp import ShardedLinearMX
+
+    n = 0
+    for blk in model.blocks:
+        if not isinstance(blk, LlamaBlock):
+            continue   # a LOCO trial replaced this block by Identity
+        for name in ("wqkv", "wo", "w13", "w2"):
+            w = getattr(blk, name)
+            setattr(blk, name + "_s", ShardedLinearMX(w.detach(), None, group=group, device=w.device))
+            delattr(blk, name)
+            n += 1
+        blk.sharded_mx = True
+    return n

@@ -39,11 +39,13 @@ class FlatParams:
     """Re-homes a module's parameters into flat bf16 arenas (optionally symmetric memory)."""
 
     def __init__(self, module: torch.nn.Module, device=None, world_size: int = 1, rank: int = 0,
-                 group=None, no_decay_fn=default_no_decay, use_symmetric: Optional[bool] = None):
+                 group=None, no_decay_fn=default_no_decay, use_symmetric: Optional[bool] = None, include=None):
+        """``include(name, param) -> bool`` restricts the arena to a subset of the module's parameters (e.g. the
+        replicated ones of a partly sharded model; the shards get a second, rank-local arena)."""
         params = []
         seen = set()
         for name, p in module.named_parameters():
-            if id(p) in seen:
+            if id(p) in seen or (include is not None and not include(name, p)):
                 continue
             seen.add(id(p))
             params.append((name, p))
