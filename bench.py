@@ -148,7 +148,11 @@ def ours_through_lagom(args):
     import tempfile
 
     rank = int(os.environ.get("RANK", "0"))
-    os.environ.setdefault("MAGGY_LOG_DIR", tempfile.mkdtemp(prefix=f"maggy_b200_bench_rank{rank}_"))
+    # every torchrun rank runs its own in-process experiment: each needs its own artefact directory
+    base = os.environ.get("MAGGY_LOG_DIR")
+    if base:
+        os.makedirs(base, exist_ok=True)
+    os.environ["MAGGY_LOG_DIR"] = tempfile.mkdtemp(prefix=f"maggy_b200_bench_rank{rank}_", dir=base or None)
     from maggy_b200 import experiment
     from maggy_b200.config import BaseConfig
 

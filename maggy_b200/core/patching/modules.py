@@ -6,8 +6,12 @@ wraps it in DDP / fairscale FSDP / a DeepSpeed engine. Same contract here, diffe
 * ``zero_lvl`` 0-2, module built on maggy_b200 ops (parameters accept the ``main_grad`` convention, e.g.
   everything in ``maggy_b200.models``): :class:`maggy_b200.parallel.DataParallel` — gradients are reduced
   by the fused reduce-scatter + Adam + all-gather kernel over NVLink, no DDP buckets;
-* any other ``torch.nn.Module``: stock ``DistributedDataParallel`` (NCCL on GPUs, gloo on CPU) — the
-  library baseline — with ``ZeroRedundancyOptimizer`` for ``zero_lvl`` 1-2 (see patching/optim.py);
+* any other ``torch.nn.Module`` whose parameters are all bf16 or all fp32, on GPUs: the SAME fused path — its autograd
+  gradients are adopted into a (bf16 or fp32) arena (``FlatParams.adopt_autograd_grads``) and reduced + applied by the
+  fp32-arena variant of the kernel; Adam / AdamW constructed by the user map onto it, other optimizers get one
+  all-reduce of the flat arena before their step (patching/optim.py);
+* mixed-dtype modules, CPU / gloo runs or ``MAGGY_B200_GENERIC_DP=ddp``: stock ``DistributedDataParallel`` — the
+  library baseline — with ``ZeroRedundancyOptimizer`` for ``zero_lvl`` 1-2;
 * ``zero_lvl`` 3 (fairscale / DeepSpeed are not used; ``backend="deepspeed"`` maps its ZeRO stage here): bf16
   modules get their eligible ``nn.Linear`` layers replaced by :class:`maggy_b200.parallel.fsdp.ShardedLinear` (row
   shards in symmetric memory, all-gather fused into the forward GEMM — K3) with the remaining parameters replicated
@@ -52,9 +56,15 @@ def get_maggy_ddp_wrapper(module: Type[torch.nn.Module]):
             super().__init__()
             model = _build_on_device(module, args, kwargs)
             use_cuda = torch.cuda.is_available()
-            if use_cuda and uses_maggy_ops(model):
-                from ...parallel.data_parallel import DataParallel
+            from ...parallel.data_parallel import DataParallel, arena_dtype_for
 
+            generic_ok = use_cuda and os.environ.get("MAGGY_B200_GENERIC_DP", "fused") == "fused" and \
+                arena_dtype_for(model) is not None and (not dist.is_initialized() or dist.get_backend() == "nccl")
+            if use_cuda and (uses_maggy_ops(model) or generic_ok):
+                # maggy_b200 models write gradients straight into the arena; any other bf16 / fp32 module gets its
+                # autograd gradients adopted into it — both are reduced + updated by the ONE fused NVLink kernel
+                if not uses_maggy_ops(model):
+                    model = model.cuda()
                 self.inner = DataParallel(model)
                 self.fused = True
             else:

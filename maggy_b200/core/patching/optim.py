@@ -32,8 +32,11 @@ def _find_fused_owner(params):
     return flat, params
 
 
-def make_zero_optimizer(optim_cls):
-    """``MaggyZero<Name>``: same constructor as ``optim_cls``, optimizer state sharded over the ranks."""
+def make_zero_optimizer(optim_cls, zero_lvl: int = 1):
+    """``MaggyZero<Name>``: same constructor as ``optim_cls``. Parameters that live in a fused ``DataParallel`` arena
+    get the fused (and sharded) path at every ZeRO level — there is no DDP underneath that would reduce their
+    gradients otherwise; other parameters get ``ZeroRedundancyOptimizer`` for ``zero_lvl`` 1-2 like the reference and
+    the plain optimizer for level 0."""
 
     class MaggyZeroOptimizer:
         def __new__(cls, params, *args, **kwargs):
@@ -47,7 +50,26 @@ def make_zero_optimizer(optim_cls):
                 if optim_cls is torch.optim.Adam:
                     kw.setdefault("weight_decay", 0.0)
                 return FusedAdamW(flat, **kw)
-            if dist.is_initialized() and dist.get_world_size() > 1:
+            if flat is not None:
+                # the parameters live in a fused DataParallel arena but the optimizer is not Adam(W): run the user's
+                # optimizer class unchanged and average the whole flat gradient arena with ONE collective before
+                # every step (there is no DDP underneath to do it bucket by bucket)
+                opt = optim_cls(params, *args, **kwargs)
+
+                def _reduce(optimizer, a, k, _flat=flat):
+                    _flat.adopt_autograd_grads()
+                    if _flat.world_size > 1:
+                        dist.all_reduce(_flat.grads, op=dist.ReduceOp.AVG, group=_flat.group)
+
+                opt.register_step_pre_hook(_reduce)
+                _orig_zero = opt.zero_grad
+
+                def _zero(set_to_none: bool = True, _flat=flat):
+                    _flat.start_step()     # gradients live in the arena: zero in place, keep p.grad pointing at it
+
+                opt.zero_grad = _zero
+                return opt
+            if zero_lvl in (1, 2) and dist.is_initialized() and dist.get_world_size() > 1:
                 from torch.distributed.optim import ZeroRedundancyOptimizer
 
                 names = list(optim_cls.__init__.__code__.co_varnames[2:optim_cls.__init__.__code__.co_argcount])
@@ -67,14 +89,11 @@ MaggyZeroAdadelta, MaggyZeroAdagrad, MaggyZeroAdam, MaggyZeroAdamW, MaggyZeroSpa
 
 @contextlib.contextmanager
 def patched_optimizers(zero_lvl: int):
-    """Swap ``torch.optim.<X>`` for the ZeRO variants while the block runs (``zero_lvl`` in 1..2)."""
-    if zero_lvl not in (1, 2):
-        yield
-        return
+    """Swap ``torch.optim.<X>`` for the maggy variants while the block runs (scoped, not process-wide)."""
     saved = {n: getattr(torch.optim, n) for n in _ZERO_CLASSES}
     try:
         for n in _ZERO_CLASSES:
-            setattr(torch.optim, n, make_zero_optimizer(saved[n]))
+            setattr(torch.optim, n, make_zero_optimizer(saved[n], zero_lvl))
         yield
     finally:
         for n, cls in saved.items():

@@ -129,6 +129,84 @@ MG_DEVICE void end_barrier(const RsAdamArgs& a) {
   }
 }
 
+MG_DEVICE float4 multimem_ld_reduce_f32x4(const void* mc_addr) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(mc_addr)
+               : "memory");
+  return r;
+}
+
+// fp32 arenas (generic torch modules: fp32 parameters, fp32 autograd gradients). The pointers in RsAdamArgs are
+// reinterpreted as float arrays; `master` is this rank's shard of its OWN parameter arena (the arena is the master).
+template <bool USE_MC>
+__global__ void __launch_bounds__(256)
+rs_adam_f32_kernel(const RsAdamArgs a_in) {
+  RsAdamArgs a = a_in;
+  if (a.epoch == 0) a.epoch = *reinterpret_cast<volatile uint32_t*>(a.local_sync + 2) + 1;
+  a.h = adam_resolve(a.h);
+  begin_barrier(a);
+  const float clip = adam_clip_coef(a.h);
+  const long long nvec = a.shard_elems >> 3;
+  const long long base = static_cast<long long>(a.rank) * a.shard_elems;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long e = base + i * 8;
+    float gf[8];
+    if constexpr (USE_MC) {
+      const float* mc = reinterpret_cast<const float*>(a.grad_mc);
+      const float4 g0 = multimem_ld_reduce_f32x4(mc + e), g1 = multimem_ld_reduce_f32x4(mc + e + 4);
+      gf[0] = g0.x; gf[1] = g0.y; gf[2] = g0.z; gf[3] = g0.w; gf[4] = g1.x; gf[5] = g1.y; gf[6] = g1.z; gf[7] = g1.w;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) gf[t] = 0.f;
+      uint4 g[kMaxWorld][2];
+#pragma unroll
+      for (int r = 0; r < kMaxWorld; ++r) {
+        if (r < a.world) {
+          int src = a.rank + r;
+          if (src >= a.world) src -= a.world;
+          const float* gp = reinterpret_cast<const float*>(a.grad_peer[src]) + e;
+          g[r][0] = ld_relaxed_sys_v4(gp);
+          g[r][1] = ld_relaxed_sys_v4(gp + 4);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kMaxWorld; ++r) {
+        if (r < a.world) {
+          gf[0] += __uint_as_float(g[r][0].x); gf[1] += __uint_as_float(g[r][0].y);
+          gf[2] += __uint_as_float(g[r][0].z); gf[3] += __uint_as_float(g[r][0].w);
+          gf[4] += __uint_as_float(g[r][1].x); gf[5] += __uint_as_float(g[r][1].y);
+          gf[6] += __uint_as_float(g[r][1].z); gf[7] += __uint_as_float(g[r][1].w);
+        }
+      }
+    }
+    const float wd = (e < a.h.decay_boundary) ? a.h.weight_decay : 0.f;
+    float p[8];
+    adam_update8_f32(a.master + i * 8, a.m + i * 8, a.v + i * 8, gf, a.h, wd, clip, p);
+    const uint4 o0 = make_uint4(__float_as_uint(p[0]), __float_as_uint(p[1]), __float_as_uint(p[2]), __float_as_uint(p[3]));
+    const uint4 o1 = make_uint4(__float_as_uint(p[4]), __float_as_uint(p[5]), __float_as_uint(p[6]), __float_as_uint(p[7]));
+    if constexpr (USE_MC) {
+      float* mc = reinterpret_cast<float*>(a.param_mc);
+      multimem_st_v4(mc + e, o0);
+      multimem_st_v4(mc + e + 4, o1);
+    } else {
+#pragma unroll
+      for (int r = 1; r < kMaxWorld; ++r) {   // r = 0 is this rank: adam_update8_f32 already wrote its arena
+        if (r < a.world) {
+          int dst = a.rank + r;
+          if (dst >= a.world) dst -= a.world;
+          float* pp = reinterpret_cast<float*>(a.param_peer[dst]) + e;
+          st_na_v4(pp, o0);
+          st_na_v4(pp + 4, o1);
+        }
+      }
+    }
+  }
+  end_barrier(a);
+}
+
 template <bool USE_MC>
 __global__ void __launch_bounds__(256)
 rs_adam_kernel(const RsAdamArgs a_in) {
@@ -199,7 +277,43 @@ rs_adam_kernel(const RsAdamArgs a_in) {
 // flag buffers must hold >= 32 zero-initialised uint32 words; local_sync >= 2 zeroed uint32 words.
 // epoch must increase by one per call on every rank (start at 1), or be 0 on every rank to use the
 // device-side launch counter (CUDA-graph replay safe).
+static int rs_adam_launch(bool fp32, const unsigned long long* grad_ptrs, const unsigned long long* param_ptrs,
+                          const unsigned long long* flag_ptrs, unsigned long long grad_mc,
+                          unsigned long long param_mc, float* master, float* m, float* v,
+                          void* local_sync, long long shard_elems, int rank, int world,
+                          unsigned int epoch, long long decay_boundary, float lr, float beta1,
+                          float beta2, float eps, float weight_decay, int step, float grad_scale,
+                          const float* gnorm_sq, float max_norm, const int* step_ptr,
+                          const float* lr_ptr, int num_ctas, void* stream);
+
+// fp32 arenas: grad / param pointers address float arrays, `master` = this rank's shard of its own parameter arena
+extern "C" int mg_rs_adam_f32(const unsigned long long* grad_ptrs, const unsigned long long* param_ptrs,
+                              const unsigned long long* flag_ptrs, unsigned long long grad_mc,
+                              unsigned long long param_mc, float* master, float* m, float* v,
+                              void* local_sync, long long shard_elems, int rank, int world,
+                              unsigned int epoch, long long decay_boundary, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, int step, float grad_scale,
+                              const float* gnorm_sq, float max_norm, const int* step_ptr,
+                              const float* lr_ptr, int num_ctas, void* stream) {
+  return rs_adam_launch(true, grad_ptrs, param_ptrs, flag_ptrs, grad_mc, param_mc, master, m, v, local_sync, shard_elems,
+                        rank, world, epoch, decay_boundary, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                        gnorm_sq, max_norm, step_ptr, lr_ptr, num_ctas, stream);
+}
+
 extern "C" int mg_rs_adam(const unsigned long long* grad_ptrs, const unsigned long long* param_ptrs,
+                          const unsigned long long* flag_ptrs, unsigned long long grad_mc,
+                          unsigned long long param_mc, float* master, float* m, float* v,
+                          void* local_sync, long long shard_elems, int rank, int world,
+                          unsigned int epoch, long long decay_boundary, float lr, float beta1,
+                          float beta2, float eps, float weight_decay, int step, float grad_scale,
+                          const float* gnorm_sq, float max_norm, const int* step_ptr,
+                          const float* lr_ptr, int num_ctas, void* stream) {
+  return rs_adam_launch(false, grad_ptrs, param_ptrs, flag_ptrs, grad_mc, param_mc, master, m, v, local_sync,
+                        shard_elems, rank, world, epoch, decay_boundary, lr, beta1, beta2, eps, weight_decay, step,
+                        grad_scale, gnorm_sq, max_norm, step_ptr, lr_ptr, num_ctas, stream);
+}
+
+static int rs_adam_launch(bool fp32, const unsigned long long* grad_ptrs, const unsigned long long* param_ptrs,
                           const unsigned long long* flag_ptrs, unsigned long long grad_mc,
                           unsigned long long param_mc, float* master, float* m, float* v,
                           void* local_sync, long long shard_elems, int rank, int world,
@@ -231,7 +345,10 @@ extern "C" int mg_rs_adam(const unsigned long long* grad_ptrs, const unsigned lo
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (grad_mc != 0 && param_mc != 0)
+  if (fp32) {
+    if (grad_mc != 0 && param_mc != 0) rs_adam_f32_kernel<true><<<grid, 256, 0, s>>>(a);
+    else rs_adam_f32_kernel<false><<<grid, 256, 0, s>>>(a);
+  } else if (grad_mc != 0 && param_mc != 0)
     rs_adam_kernel<true><<<grid, 256, 0, s>>>(a);
   else
     rs_adam_kernel<false><<<grid, 256, 0, s>>>(a);

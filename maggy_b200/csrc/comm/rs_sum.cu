@@ -140,7 +140,84 @@ rs_sum_kernel(const RsSumArgs a_in) {
   }
 }
 
+// K2 — one-shot broadcast of a buffer from `root` to every rank over NVLink (DDP's constructor broadcast, SURVEY C3;
+// reference maggy/core/patching/modules.py:62-63): the root's CTAs read their own copy once and store it to all peers
+// — ONE multimem.st per 16 bytes when a multicast address is bound (the switch replicates), else `world - 1` peer
+// stores; the other ranks' kernels only wait for the root's end flag. Flag words [16..24) / [24..32) of the same
+// symmetric flag buffer are used so that broadcasts and reductions can share it.
+struct BcastArgs {
+  uint8_t* buf_peer[kMaxWorld];
+  uint32_t* flag_peer[kMaxWorld];
+  uint8_t* buf_mc;
+  uint32_t* local_sync;   // [1] finished-CTA counter
+  long long bytes;        // multiple of 16
+  int rank, world, root;
+  uint32_t epoch;
+};
+
+__global__ void __launch_bounds__(256)
+peer_bcast_kernel(const BcastArgs a) {
+  if (a.rank == a.root) {
+    const long long nvec = a.bytes >> 4;
+    const uint4* src = reinterpret_cast<const uint4*>(a.buf_peer[a.root]);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const uint4 v = src[i];
+      if (a.buf_mc != nullptr) {
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.buf_mc + i * 16), "r"(v.x),
+                     "r"(v.y), "r"(v.z), "r"(v.w)
+                     : "memory");
+      } else {
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r)
+          if (r < a.world && r != a.root) st_na_v4(a.buf_peer[r] + i * 16, v);
+      }
+    }
+    __syncthreads();
+    __shared__ uint32_t is_last;
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      is_last = (atomicAdd(a.local_sync + 1, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (is_last) {
+      if (threadIdx.x == 0) a.local_sync[1] = 0;
+      if (threadIdx.x < a.world) {
+        __threadfence_system();
+        st_release_sys_u32(a.flag_peer[threadIdx.x] + 16 + a.root, a.epoch);
+      }
+    }
+  } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+    spin_until([&] { return ld_acquire_sys_u32(a.flag_peer[a.rank] + 16 + a.root) >= a.epoch; }, "broadcast root");
+  }
+}
+
 }  // namespace
+
+// buf_ptrs / flag_ptrs: `world` peer-mapped pointers (symmetric buffers; flags >= 32 zeroed uint32); buf_mc: multicast
+// address of the buffer or 0. `epoch` must increase with every call on every rank.
+extern "C" int mg_peer_bcast(const unsigned long long* buf_ptrs, const unsigned long long* flag_ptrs,
+                             unsigned long long buf_mc, void* local_sync, long long bytes, int rank, int world, int root,
+                             unsigned int epoch, void* stream) {
+  if (world < 1 || world > kMaxWorld || bytes % 16 != 0 || root < 0 || root >= world) return -1;
+  BcastArgs a;
+  for (int r = 0; r < kMaxWorld; ++r) {
+    a.buf_peer[r] = r < world ? reinterpret_cast<uint8_t*>(buf_ptrs[r]) : nullptr;
+    a.flag_peer[r] = r < world ? reinterpret_cast<uint32_t*>(flag_ptrs[r]) : nullptr;
+  }
+  a.buf_mc = reinterpret_cast<uint8_t*>(buf_mc);
+  a.local_sync = static_cast<uint32_t*>(local_sync);
+  a.bytes = bytes; a.rank = rank; a.world = world; a.root = root; a.epoch = epoch;
+  int grid = 1;
+  if (rank == root) {
+    grid = static_cast<int>(((bytes >> 4) + 255) / 256);
+    if (grid > 148 * 2) grid = 148 * 2;
+    if (grid < 1) grid = 1;
+  }
+  peer_bcast_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
+}
 
 // in_ptrs / flag_ptrs: host arrays of `world` peer-mapped device pointers (full buffers of world * shard_elems bf16,
 // flag buffers of >= 32 zeroed uint32); local_sync: 4 zeroed uint32; in_mc: multicast address of the input or 0.

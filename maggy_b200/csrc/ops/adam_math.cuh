@@ -53,13 +53,13 @@ MG_DEVICE float adam_clip_coef(const AdamHyper& h) {
 }
 
 // Update 8 consecutive elements. master/m/v are fp32 (read-modify-write), gf is the fp32 gradient,
-// `out` receives the 8 updated parameters packed as bf16.
-MG_DEVICE void adam_update8(float* master, float* m, float* v, const float (&gf)[8],
-                            const AdamHyper& h, float wd, float clip, uint4& out) {
+// `p` receives the 8 updated parameters in fp32.
+MG_DEVICE void adam_update8_f32(float* master, float* m, float* v, const float (&gf)[8],
+                                const AdamHyper& h, float wd, float clip, float (&p)[8]) {
   float4 p0 = reinterpret_cast<float4*>(master)[0], p1 = reinterpret_cast<float4*>(master)[1];
   float4 m0 = reinterpret_cast<float4*>(m)[0], m1 = reinterpret_cast<float4*>(m)[1];
   float4 v0 = reinterpret_cast<float4*>(v)[0], v1 = reinterpret_cast<float4*>(v)[1];
-  float p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+  p[0] = p0.x; p[1] = p0.y; p[2] = p0.z; p[3] = p0.w; p[4] = p1.x; p[5] = p1.y; p[6] = p1.z; p[7] = p1.w;
   float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
   float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
   const float gs = h.grad_scale * clip;
@@ -80,6 +80,13 @@ MG_DEVICE void adam_update8(float* master, float* m, float* v, const float (&gf)
   reinterpret_cast<float4*>(m)[1] = make_float4(mm[4], mm[5], mm[6], mm[7]);
   reinterpret_cast<float4*>(v)[0] = make_float4(vv[0], vv[1], vv[2], vv[3]);
   reinterpret_cast<float4*>(v)[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+}
+
+// Same, `out` receives the 8 updated parameters packed as bf16 (the compute copy of a bf16 arena).
+MG_DEVICE void adam_update8(float* master, float* m, float* v, const float (&gf)[8],
+                            const AdamHyper& h, float wd, float clip, uint4& out) {
+  float p[8];
+  adam_update8_f32(master, m, v, gf, h, wd, clip, p);
   out = make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]),
                    pack_bf16x2(p[6], p[7]));
 }

@@ -35,6 +35,35 @@ adam_flat_kernel(float* __restrict__ master, float* __restrict__ m, float* __res
   }
 }
 
+// fp32 arena (generic torch modules keep fp32 parameters): the parameter arena IS the master copy, gradients are fp32
+__global__ void __launch_bounds__(256)
+adam_flat_f32_kernel(float* __restrict__ param, float* __restrict__ m, float* __restrict__ v,
+                     const float* __restrict__ grad, long long n, AdamHyper h_in) {
+  const AdamHyper h = adam_resolve(h_in);
+  const float clip = adam_clip_coef(h);
+  const long long nvec = n >> 3;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 g0 = reinterpret_cast<const float4*>(grad)[2 * i], g1 = reinterpret_cast<const float4*>(grad)[2 * i + 1];
+    const float gf[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float wd = (i * 8 < h.decay_boundary) ? h.weight_decay : 0.f;
+    float p[8];
+    adam_update8_f32(param + i * 8, m + i * 8, v + i * 8, gf, h, wd, clip, p);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_f32_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < (n >> 2);
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(x)[i];
+    acc += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 // sum of squares of a bf16 arena into *out (fp32, must be zeroed by the caller)
 __global__ void __launch_bounds__(256)
 sumsq_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long n, float* __restrict__ out) {
@@ -95,6 +124,32 @@ extern "C" int mg_adam_flat(float* master, float* m, float* v, const void* grad,
   adam_flat_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       master, m, v, reinterpret_cast<const __nv_bfloat16*>(grad),
       reinterpret_cast<__nv_bfloat16*>(param_bf16), n, h);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
+}
+
+extern "C" int mg_adam_flat_f32(float* param, float* m, float* v, const float* grad, long long n,
+                                long long decay_boundary, float lr, float beta1, float beta2, float eps,
+                                float weight_decay, int step, float grad_scale, const float* gnorm_sq, float max_norm,
+                                const int* step_ptr, const float* lr_ptr, void* stream) {
+  if (n % 8 != 0) return -1;
+  AdamHyper h = make_adam_hyper(lr, beta1, beta2, eps, weight_decay, step, grad_scale, decay_boundary, gnorm_sq, max_norm);
+  h.step_ptr = step_ptr;
+  h.lr_ptr = lr_ptr;
+  int grid = static_cast<int>(((n >> 3) + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  adam_flat_f32_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(param, m, v, grad, n, h);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
+}
+
+extern "C" int mg_sumsq_f32(const float* x, long long n, float* out, void* stream) {
+  if (n % 4 != 0) return -1;
+  int grid = static_cast<int>(((n >> 2) + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  sumsq_f32_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n, out);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
 }

@@ -70,6 +70,9 @@ def cuda():
         _sig(lib.mg_adam_flat, [P, P, P, P, P, c_ll, c_ll, c_float, c_float, c_float, c_float,
                                 c_float, c_int, c_float, P, c_float, P, P, P])
         _sig(lib.mg_sumsq_bf16, [P, c_ll, P, P])
+        _sig(lib.mg_sumsq_f32, [P, c_ll, P, P])
+        _sig(lib.mg_adam_flat_f32, [P, P, P, P, c_ll, c_ll, c_float, c_float, c_float, c_float, c_float, c_int, c_float,
+                                    P, c_float, P, P, P])
         _sig(lib.mg_cast_f32_bf16, [P, P, c_ll, P])
         _sig(lib.mg_ce_fwd_bwd, [P, P, P, c_int, c_int, c_int, c_ll, c_float, P, c_int, P])
         _sig(lib.mg_colsum_slabs, [c_int])

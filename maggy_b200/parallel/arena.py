@@ -39,9 +39,15 @@ class FlatParams:
     """Re-homes a module's parameters into flat bf16 arenas (optionally symmetric memory)."""
 
     def __init__(self, module: torch.nn.Module, device=None, world_size: int = 1, rank: int = 0,
-                 group=None, no_decay_fn=default_no_decay, use_symmetric: Optional[bool] = None, include=None):
+                 group=None, no_decay_fn=default_no_decay, use_symmetric: Optional[bool] = None, include=None,
+                 dtype=torch.bfloat16):
         """``include(name, param) -> bool`` restricts the arena to a subset of the module's parameters (e.g. the
-        replicated ones of a partly sharded model; the shards get a second, rank-local arena)."""
+        replicated ones of a partly sharded model; the shards get a second, rank-local arena).
+
+        ``dtype``: ``torch.bfloat16`` (default: bf16 compute arena + fp32 master shard) or ``torch.float32`` — generic
+        torch modules keep fp32 parameters and receive fp32 autograd gradients; their arena IS the master copy."""
+        assert dtype in (torch.bfloat16, torch.float32)
+        self.dtype = dtype
         params = []
         seen = set()
         for name, p in module.named_parameters():
@@ -72,12 +78,14 @@ class FlatParams:
         for n, p, o, k in self.entries:
             init[o:o + k].copy_(p.detach().reshape(-1).to(device=self.device, dtype=torch.float32))
 
-        self.params = self._alloc("params", self.numel, torch.bfloat16)
-        self.grads = self._alloc("grads", self.numel, torch.bfloat16)
-        self.params.copy_(init.to(torch.bfloat16))
+        self.params = self._alloc("params", self.numel, dtype)
+        self.grads = self._alloc("grads", self.numel, dtype)
+        self.params.copy_(init.to(dtype))
         self.grads.zero_()
         lo = self.rank * self.shard_numel
-        self.master = init[lo:lo + self.shard_numel].clone()
+        # bf16 arena: separate fp32 master shard. fp32 arena: the rank's slice of the arena itself
+        self.master = init[lo:lo + self.shard_numel].clone() if dtype == torch.bfloat16 else \
+            self.params[lo:lo + self.shard_numel]
         del init
         for n, p, o, k in self.entries:
             p.data = self.params[o:o + k].view(p.shape)
@@ -206,13 +214,13 @@ class FusedAdamW:
                 use_multicast = (env == "1") if env in ("0", "1") else W >= 4
             self._grad_mc = flat.multicast_ptr("grads") if use_multicast else 0
             self._param_mc = flat.multicast_ptr("params") if use_multicast else 0
-            _lib.register_cuda_symbol(
-                "mg_rs_adam",
-                [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_ulonglong,
-                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
-                 ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.c_longlong, ctypes.c_float, ctypes.c_float,
-                 ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
-                 ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p])
+            sig = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_ulonglong,
+                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
+                   ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.c_longlong, ctypes.c_float, ctypes.c_float,
+                   ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
+                   ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+            for sym in ("mg_rs_adam", "mg_rs_adam_f32"):
+                _lib.register_cuda_symbol(sym, sig)
             # make sure every rank zeroed its flags before anyone signals
             torch.cuda.synchronize(dev)
             torch.distributed.barrier(group=flat.group)
@@ -234,7 +242,12 @@ class FusedAdamW:
         if self.max_grad_norm > 0:
             # local sum of squares of the local gradient; exact global norm needs the reduced gradient,
             # so for world > 1 we clip on the all-reduced norm of the *local* shards' contributions.
-            F.sumsq(flat.grads, self.gnorm_sq)
+            if flat.dtype == torch.float32:
+                self.gnorm_sq.zero_()
+                _lib.check(_lib.cuda().mg_sumsq_f32(flat.grads.data_ptr(), flat.grads.numel(), self.gnorm_sq.data_ptr(),
+                                                    F._stream()), "mg_sumsq_f32")
+            else:
+                F.sumsq(flat.grads, self.gnorm_sq)
             if flat.world_size > 1:
                 torch.distributed.all_reduce(self.gnorm_sq, group=flat.group)
             gn = self.gnorm_sq
@@ -243,7 +256,16 @@ class FusedAdamW:
         if self.graph_safe:
             self.step_tensor += 1  # captured as a tiny kernel: the replayed graph advances the step
             st, lt = self.step_tensor, self.lr_tensor
-        if flat.world_size == 1:
+        if flat.world_size == 1 and flat.dtype == torch.float32:
+            rc = _lib.cuda().mg_adam_flat_f32(flat.params.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                              flat.grads.data_ptr(), flat.numel, flat.decay_boundary, lr, b1, b2, self.eps,
+                                              self.weight_decay, self.step_count, self.grad_scale,
+                                              0 if gn is None else gn.data_ptr(), self.max_grad_norm,
+                                              0 if st is None else st.data_ptr(), 0 if lt is None else lt.data_ptr(),
+                                              F._stream())
+            _lib.check(rc, "mg_adam_flat_f32")
+            F._count(1)
+        elif flat.world_size == 1:
             F.adam_flat_step(flat.master, self.m, self.v, flat.grads, flat.params,
                              decay_boundary=flat.decay_boundary, lr=lr, beta1=b1, beta2=b2, eps=self.eps,
                              weight_decay=self.weight_decay, step=self.step_count,
@@ -251,7 +273,8 @@ class FusedAdamW:
                              step_tensor=st, lr_tensor=lt)
         else:
             self.epoch += 1
-            rc = _lib.cuda().mg_rs_adam(
+            kernel = _lib.cuda().mg_rs_adam_f32 if flat.dtype == torch.float32 else _lib.cuda().mg_rs_adam
+            rc = kernel(
                 self._grad_ptrs, self._param_ptrs, self._flag_ptrs, self._grad_mc, self._param_mc,
                 flat.master.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.local_sync.data_ptr(),
                 flat.shard_numel, flat.rank, flat.world_size, 0 if self.graph_safe else self.epoch,
