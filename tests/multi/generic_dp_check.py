@@ -34,8 +34,9 @@ def main():
         Wrapped = get_maggy_ddp_wrapper(MLP)
         model = Wrapped()
         assert model.fused, "generic fp32 module did not take the fused path"
-        torch.manual_seed(1234)               # oracle = rank 0's initialisation
-        ref = MLP().to(dev)
+        torch.manual_seed(1234)               # oracle = rank 0's initialisation (built on the device, like the wrapper)
+        with torch.device(dev):
+            ref = MLP()
         for (n1, p1), (n2, p2) in zip(model.inner.module.named_parameters(), ref.named_parameters()):
             assert torch.equal(p1.detach(), p2.detach()), f"K2 broadcast: {n1} differs from rank 0's value"
         ref = torch.nn.parallel.DistributedDataParallel(ref, device_ids=[dev.index])
