@@ -41,13 +41,14 @@ def make_zero_optimizer(optim_cls, zero_lvl: int = 1):
     class MaggyZeroOptimizer:
         def __new__(cls, params, *args, **kwargs):
             flat, params = _find_fused_owner(params)
-            if flat is not None and optim_cls in (torch.optim.Adam, torch.optim.AdamW):
+            # (by name: inside patched_optimizers() torch.optim.Adam IS the patched class, not the saved original)
+            if flat is not None and optim_cls.__name__ in ("Adam", "AdamW"):
                 from ...parallel.arena import FusedAdamW
 
                 names = ("lr", "betas", "eps", "weight_decay")
                 kw = dict(zip(names, args))
                 kw.update({k: v for k, v in kwargs.items() if k in names})
-                if optim_cls is torch.optim.Adam:
+                if optim_cls.__name__ == "Adam":
                     kw.setdefault("weight_decay", 0.0)
                 return FusedAdamW(flat, **kw)
             if flat is not None:
