@@ -50,6 +50,12 @@ def _wrap_module_dispatcher(config):
     module = config.module
     if module is None:
         return None
+    if getattr(config, "backend", "torch") == "deepspeed" and config.deepspeed_config:
+        # an engine with DeepSpeed's API (backward / step / loss scaling) on the fused data plane
+        wrap_ds = lambda m: pm.get_maggy_deepspeed_wrapper(m, config.deepspeed_config)  # noqa: E731
+        if isinstance(module, (list, tuple)):
+            return type(module)(wrap_ds(m) for m in module)
+        return wrap_ds(module)
     if config.zero_lvl >= 3:
         wrap = lambda m: pm.get_maggy_fsdp_wrapper(m, config.mixed_precision)  # noqa: E731
     else:

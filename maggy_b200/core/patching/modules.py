@@ -134,9 +134,16 @@ get_maggy_fairscale_wrapper = get_maggy_fsdp_wrapper
 
 
 def get_maggy_deepspeed_wrapper(module: Type[torch.nn.Module], config_params: dict):
-    """DeepSpeed configs are honoured for their ZeRO stage and fp16/bf16 switches only."""
-    stage = int(config_params.get("zero_optimization", {}).get("stage", 0))
-    mixed = bool(config_params.get("fp16", {}).get("enabled") or config_params.get("bf16", {}).get("enabled"))
+    """``backend="deepspeed"``: an engine with DeepSpeed's train-loop API (``engine(x)``, ``engine.backward(loss)``,
+    ``engine.step()``), its optimizer section, fp16 loss scaling, gradient accumulation and clipping, running on the
+    fused NVLink data plane (patching/deepspeed_engine.py). Configs without an ``optimizer`` section keep the round-1
+    behaviour: only the ZeRO stage and the 16-bit switch are honoured and the train_fn builds its own optimizer."""
     if getattr(module, "__name__", "") == "PipelineModule":
         raise AssertionError("Maggy does not support pipeline parallelism (reference modules.py:106-109)")
+    if "optimizer" in (config_params or {}):
+        from .deepspeed_engine import get_maggy_deepspeed_engine
+
+        return get_maggy_deepspeed_engine(module, config_params)
+    stage = int(config_params.get("zero_optimization", {}).get("stage", 0))
+    mixed = bool(config_params.get("fp16", {}).get("enabled") or config_params.get("bf16", {}).get("enabled"))
     return get_maggy_fsdp_wrapper(module, mixed) if stage >= 3 else get_maggy_ddp_wrapper(module)
