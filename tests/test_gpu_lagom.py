@@ -82,7 +82,8 @@ def test_device_scheduler_stops_trials_during_a_real_lagom_run(tmp_path, monkeyp
     res = experiment.lagom(train_constant_quality_on_device, cfg)
     EnvSing.reset()
     root = str(tmp_path / "experiment_log")
-    run = os.path.join(root, os.listdir(root)[0], "1")
+    app = os.path.join(root, sorted(os.listdir(root))[-1])
+    run = os.path.join(app, sorted(os.listdir(app), key=int)[-1])   # RUN_ID keeps counting within a process
     meta = json.load(open(os.path.join(run, "maggy.json")))
     log = open(os.path.join(run, "maggy.log")).read()
     k9 = meta.get("device_scheduler")

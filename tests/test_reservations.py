@@ -52,15 +52,17 @@ def test_driver_channel_keeps_reservations_in_sync():
         ch.close()
 
 
-def test_tf_front_end_raises_not_supported():
+def test_tf_front_end_needs_tensorflow_only_at_run_time(monkeypatch):
+    """The TF stack is implemented (tests/test_tf_distributed.py); TensorFlow itself is optional and its absence
+    surfaces as NotSupportedError when a worker tries to import it."""
     from maggy_b200.core.exceptions import NotSupportedError
-    from maggy_b200.core.executors.tf_dist_executor import tf_dist_executor_fn
+    from maggy_b200.core.executors.tf_dist_executor import import_tensorflow
     from maggy_b200.core.tf_patching import get_wrapped_model
 
+    monkeypatch.setenv("MAGGY_B200_TF_MODULE", "definitely_not_tensorflow")
     with pytest.raises(NotSupportedError):
-        tf_dist_executor_fn(None, None)
-    with pytest.raises(NotSupportedError):
-        get_wrapped_model(object)
+        import_tensorflow()
+    assert get_wrapped_model(None, None, False) is None
 
 
 def test_runtime_mode_flags():

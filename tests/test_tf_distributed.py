@@ -115,7 +115,8 @@ def test_lagom_tf_distributed_end_to_end_with_stand_in(_tf_env, monkeypatch):
     expected = sorted([sum([x * 2 for x in range(12)][0::2]), sum([x * 2 for x in range(12)][1::2]), full])
     assert res["test result"] == pytest.approx(sum(expected) / 3)
     root = str(_tf_env / "experiment_log")
-    run = os.path.join(root, os.listdir(root)[0], "1")
+    app = os.path.join(root, sorted(os.listdir(root))[-1])
+    run = os.path.join(app, sorted(os.listdir(app), key=int)[-1])   # RUN_ID keeps counting within a process
     meta = json.load(open(os.path.join(run, "maggy.json")))
     assert meta["experiment_type"] == "tf_dist" and meta["executors"] == 3
     assert sorted(meta["cluster"]) == ["chief", "evaluator", "worker"]
