@@ -1,4 +1,5 @@
-"""fp8 (e4m3) tcgen05 GEMM vs our bf16 GEMM vs cuBLASLt fp8 (torch._scaled_mm). CUDA events, L2 flushed."""
+"""fp8 (e4m3, per-tensor) and block-scaled MXFP8 tcgen05 GEMMs vs our bf16 GEMM vs cuBLASLt fp8 (torch._scaled_mm).
+CUDA events, L2 flushed."""
 import os
 import sys
 
@@ -20,6 +21,10 @@ for name, M, N, K in [("fc 32768x3072x768", 32768, 3072, 768), ("fc2 32768x768x3
     t8 = timeit(lambda: F.gemm_fp8(aq, bq, sa, sb, out=out), flush)
     t16 = timeit(lambda: F.gemm(a, b, out=out), flush)
     tq = timeit(lambda: F.quantize_fp8(a), flush)
+    am, sfa = F.quantize_mxfp8(a)
+    bm, sfb = F.quantize_mxfp8(b)
+    tmx = timeit(lambda: F.gemm_mxfp8(am, sfa, bm, sfb, out=out), flush)
+    tqm = timeit(lambda: F.quantize_mxfp8(a), flush)
     try:
         tl = timeit(lambda: torch._scaled_mm(aq, bq.t(), scale_a=sa, scale_b=sb, out_dtype=torch.bfloat16), flush)
     except Exception as e:  # noqa: BLE001
@@ -27,4 +32,5 @@ for name, M, N, K in [("fc 32768x3072x768", 32768, 3072, 768), ("fc2 32768x768x3
         print("scaled_mm:", str(e)[:100])
     fl = 2.0 * M * N * K
     print(f"{name:30s} fp8 ours {t8:7.3f} ms ({fl / t8 / 1e9:6.0f} TF)  bf16 ours {t16:7.3f} ms ({fl / t16 / 1e9:6.0f} TF)"
-          f"  cuBLASLt fp8 {tl:7.3f} ms ({fl / tl / 1e9:6.0f} TF)  quantise(A) {tq:6.3f} ms", flush=True)
+          f"  cuBLASLt fp8 {tl:7.3f} ms ({fl / tl / 1e9:6.0f} TF)  quantise(A) {tq:6.3f} ms"
+          f" | mxfp8 (block-scaled) ours {tmx:7.3f} ms ({fl / tmx / 1e9:6.0f} TF)  mx quantise(A) {tqm:6.3f} ms", flush=True)
