@@ -60,9 +60,12 @@ class BertLayer(nn.Module):
             y = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2),
                                                                  v.transpose(1, 2), attn_mask=attn_mask)
             y = y.transpose(1, 2).reshape(B, T, C)
-        x = F.layer_norm(F.linear(y, self.o_w, self.o_b, residual=x), self.ln1_w, self.ln1_b, self.eps)
+        # post-LN: each norm is the only consumer of the linear / MLP output before it, so its backward also yields that
+        # layer's bias gradient (col_bias) and no separate column-sum pass runs
+        x = F.layer_norm(F.linear(y, self.o_w, self.o_b, residual=x), self.ln1_w, self.ln1_b, self.eps,
+                         col_bias=self.o_b)
         x = F.layer_norm(F.mlp(x, self.fc_w, self.fc_b, self.fc2_w, self.fc2_b, residual=x), self.ln2_w, self.ln2_b,
-                         self.eps)
+                         self.eps, col_bias=self.fc2_b)
         return x
 
 

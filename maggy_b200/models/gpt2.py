@@ -64,6 +64,8 @@ class Block(nn.Module):
         self.eps = cfg.layer_norm_eps
         self.attn_impl = _attn_impl(cfg)
         self.fold_residual_grad = __import__("os").environ.get("MAGGY_B200_LN_RES", "1") != "0"
+        # bias gradients of proj / fc2 come out of the norm backward that consumes their output (no colsum pass)
+        self.fold_bias_grad = self.fold_residual_grad and __import__("os").environ.get("MAGGY_B200_LN_COL", "1") != "0"
         self.ln1_w = nn.Parameter(torch.ones(C))
         self.ln1_b = nn.Parameter(torch.zeros(C))
         self.qkv_w = nn.Parameter(torch.empty(3 * C, C))
@@ -77,12 +79,15 @@ class Block(nn.Module):
         self.fc2_w = nn.Parameter(torch.empty(C, 4 * C))
         self.fc2_b = nn.Parameter(torch.zeros(C))
 
-    def forward(self, x):
+    def forward(self, x, prev_bias=None):
+        """``prev_bias``: bias of the layer that produced ``x`` (the previous block's ``fc2_b``), or None."""
         B, T, C = x.shape
         H = self.n_head
         # x_res aliases x: routing the residual through the norm op folds the residual-gradient add into its backward
         fold = self.fold_residual_grad
-        h, x_res = F.layer_norm(x, self.ln1_w, self.ln1_b, self.eps, with_residual=True) if fold else \
+        colb = self.fold_bias_grad
+        h, x_res = F.layer_norm(x, self.ln1_w, self.ln1_b, self.eps, with_residual=True,
+                                col_bias=prev_bias if colb else None) if fold else \
             (F.layer_norm(x, self.ln1_w, self.ln1_b, self.eps), x)
         qkv = F.linear(h, self.qkv_w, self.qkv_b)
         if self.attn_impl == "native" and C // H == 64 and qkv.is_cuda:
@@ -94,7 +99,8 @@ class Block(nn.Module):
                 q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True)
             y = y.transpose(1, 2).reshape(B, T, C)
         x = F.linear(y, self.proj_w, self.proj_b, residual=x_res)   # x + attn (residual fused)
-        h, x_res = F.layer_norm(x, self.ln2_w, self.ln2_b, self.eps, with_residual=True) if fold else \
+        h, x_res = F.layer_norm(x, self.ln2_w, self.ln2_b, self.eps, with_residual=True,
+                                col_bias=self.proj_b if colb else None) if fold else \
             (F.layer_norm(x, self.ln2_w, self.ln2_b, self.eps), x)
         x = F.mlp(h, self.fc_w, self.fc_b, self.fc2_w, self.fc2_b, residual=x_res)  # x + mlp
         return x
@@ -139,9 +145,13 @@ class GPT2(nn.Module):
 
     def forward(self, idx, targets=None):
         x = F.embedding(idx, self.wte, self.wpe)
+        prev_bias = None
         for blk in self.blocks:
-            x = blk(x)
-        x = F.layer_norm(x, self.lnf_w, self.lnf_b, self.cfg.layer_norm_eps)
+            x = blk(x, prev_bias)
+            prev_bias = blk.fc2_b
+        last = self.blocks[-1] if len(self.blocks) else None
+        x = F.layer_norm(x, self.lnf_w, self.lnf_b, self.cfg.layer_norm_eps,
+                         col_bias=last.fc2_b if last is not None and last.fold_bias_grad else None)
         logits = F.linear(x, self.wte)  # tied LM head: [B, T, padded_vocab]
         if targets is None:
             return logits

@@ -67,6 +67,8 @@ def cuda():
         _sig(lib.mg_norm_bwd_grid, [c_int])
         _sig(lib.mg_norm_bwd, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P])
         _sig(lib.mg_norm_bwd_res, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P])
+        _sig(lib.mg_norm_bwd_col, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P])
+        _sig(lib.mg_norm_bwd_supports_col, [c_int])
         _sig(lib.mg_adam_flat, [P, P, P, P, P, c_ll, c_ll, c_float, c_float, c_float, c_float,
                                 c_float, c_int, c_float, P, c_float, P, P, P])
         _sig(lib.mg_sumsq_bf16, [P, c_ll, P, P])

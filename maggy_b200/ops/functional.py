@@ -128,9 +128,11 @@ def layer_norm_fwd(x2d, weight, bias, eps=1e-5, rms=False):
     return y, mean, rstd
 
 
-def layer_norm_bwd(dy2d, x2d, weight, mean, rstd, dgamma, dbeta, rms=False, accumulate=False, res_grad=None):
+def layer_norm_bwd(dy2d, x2d, weight, mean, rstd, dgamma, dbeta, rms=False, accumulate=False, res_grad=None,
+                   dcol=None, accumulate_col=False):
     """``res_grad`` ([rows, C] bf16, optional) is added to the returned ``dx`` inside the kernel (the gradient that
-    reaches ``x`` through a residual connection around the normalised branch)."""
+    reaches ``x`` through a residual connection around the normalised branch). ``dcol`` ([C] bf16, optional) receives
+    the column sums of that ``dx`` — the bias gradient of the layer that produced ``x`` — from the same pass."""
     _need_cuda(dy2d, x2d, res_grad)
     rows, C = x2d.shape
     dy2d = dy2d.contiguous()
@@ -142,12 +144,15 @@ def layer_norm_bwd(dy2d, x2d, weight, mean, rstd, dgamma, dbeta, rms=False, accu
     lib = _lib.cuda()
     grid = lib.mg_norm_bwd_grid(rows)
     partial = _scratch_f32("norm_bwd", grid * 2 * C, x2d.device)
-    rc = lib.mg_norm_bwd_res(dy2d.data_ptr(), x2d.data_ptr(), weight.data_ptr(), _ptr(mean),
+    fused_col = dcol is not None and bool(lib.mg_norm_bwd_supports_col(C))
+    rc = lib.mg_norm_bwd_col(dy2d.data_ptr(), x2d.data_ptr(), weight.data_ptr(), _ptr(mean),
                              rstd.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), _ptr(dbeta),
-                             partial.data_ptr(), rows, C, 1 if rms else 0, 1 if accumulate else 0, _ptr(res_grad),
-                             _stream())
+                             dcol.data_ptr() if fused_col else None, partial.data_ptr(), rows, C, 1 if rms else 0,
+                             1 if accumulate else 0, 1 if accumulate_col else 0, _ptr(res_grad), _stream())
     _lib.check(rc, "mg_norm_bwd")
     _count(2)
+    if dcol is not None and not fused_col:  # widths the staged kernel does not cover: a separate pass over dx
+        colsum(dx, dcol, accumulate=accumulate_col)
     return dx
 
 
@@ -349,7 +354,7 @@ class _Linear(torch.autograd.Function):
             ctx.weight_ref,
             lambda dst, acc: gemm(dy2, x2, a_major=MN_MAJOR, b_major=MN_MAJOR, out=dst, accumulate=acc))
         db = None
-        if ctx.bias is not None:
+        if ctx.bias is not None and not _take_norm_colsum(ctx.bias):
             db = _write_or_return_grad(ctx.bias, lambda dst, acc: colsum(dy2, dst, accumulate=acc))
         dres = dy if ctx.has_res else None
         return dx, dw, db, dres
@@ -462,13 +467,25 @@ def linear_mxfp8(x, weight, bias=None):
     return _LinearMXFP8.apply(x, weight, bias)
 
 
+def _take_norm_colsum(bias) -> bool:
+    """True when the norm that consumed this layer's output already produced ``bias``'s gradient (``col_bias=``)."""
+    if bias is not None and getattr(bias, "_colsum_in_norm", False):
+        bias._colsum_in_norm = False
+        return True
+    return False
+
+
 class _LayerNorm(torch.autograd.Function):
     """``with_residual=True`` additionally returns ``x`` itself (an alias, no kernel) as the tensor to feed into the
     residual connection around the normalised branch: both gradients then arrive in THIS backward and are summed
-    inside the norm-backward kernel instead of by a separate autograd add over the whole activation."""
+    inside the norm-backward kernel instead of by a separate autograd add over the whole activation.
+
+    ``col_bias``: the bias parameter of the ``linear`` / ``mlp`` whose output is ``x`` (and is consumed ONLY here).
+    The ``dx`` this backward writes is that layer's output gradient, so its bias gradient (column sums of ``dx``) is
+    accumulated by the same kernel and the producer skips its own reduction pass."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, rms, with_residual=False):
+    def forward(ctx, x, weight, bias, eps, rms, with_residual=False, col_bias=None):
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
@@ -477,6 +494,10 @@ class _LayerNorm(torch.autograd.Function):
         ctx.w_ref, ctx.b_ref, ctx.rms = weight, bias, rms
         ctx.xshape = x.shape
         ctx.with_residual = with_residual
+        ctx.col_bias = None
+        if col_bias is not None and ctx.needs_input_grad[0]:  # (grad mode is off inside forward: ask ctx)
+            ctx.col_bias = col_bias
+            col_bias._colsum_in_norm = True  # consumed (and cleared) by the producer's backward
         if with_residual:
             return y.view(x.shape), x.view_as(x)
         return y.view(x.shape)
@@ -500,22 +521,30 @@ class _LayerNorm(torch.autograd.Function):
             acc = False
             dgamma = torch.empty_like(w)
             dbeta = torch.empty_like(b) if b is not None else None
+        cb, dcol, acc_col, dcol_ret = ctx.col_bias, None, False, None
+        if cb is not None:
+            if getattr(cb, "main_grad", None) is not None:
+                dcol, acc_col = cb.main_grad, bool(getattr(cb, "_mg_written", False))
+                cb._mg_written = True
+            else:
+                dcol = dcol_ret = torch.empty_like(cb)
         dx = layer_norm_bwd(dy2, x2, weight, None if ctx.rms else mean, rstd, dgamma, dbeta,
-                            rms=ctx.rms, accumulate=acc, res_grad=dres if ctx.with_residual else None)
+                            rms=ctx.rms, accumulate=acc, res_grad=dres if ctx.with_residual else None,
+                            dcol=dcol, accumulate_col=acc_col)
         if use_main:
-            return dx.view(ctx.xshape), None, None, None, None, None
-        return dx.view(ctx.xshape), dgamma, dbeta, None, None, None
+            return dx.view(ctx.xshape), None, None, None, None, None, dcol_ret
+        return dx.view(ctx.xshape), dgamma, dbeta, None, None, None, dcol_ret
 
 
-def layer_norm(x, weight, bias, eps=1e-5, with_residual=False):
+def layer_norm(x, weight, bias, eps=1e-5, with_residual=False, col_bias=None):
     """``with_residual=True`` returns ``(norm(x), x_res)``: use ``x_res`` as the residual input of the branch
     (``linear(..., residual=x_res)`` / ``mlp(..., residual=x_res)``) to fold the residual-gradient add into the norm
-    backward kernel."""
-    return _LayerNorm.apply(x, weight, bias, eps, False, with_residual)
+    backward kernel. ``col_bias``: see :class:`_LayerNorm`."""
+    return _LayerNorm.apply(x, weight, bias, eps, False, with_residual, col_bias)
 
 
-def rms_norm(x, weight, eps=1e-6, with_residual=False):
-    return _LayerNorm.apply(x, weight, None, eps, True, with_residual)
+def rms_norm(x, weight, eps=1e-6, with_residual=False, col_bias=None):
+    return _LayerNorm.apply(x, weight, None, eps, True, with_residual, col_bias)
 
 
 class _MLP(torch.autograd.Function):
@@ -551,7 +580,9 @@ class _MLP(torch.autograd.Function):
         dpre = gemm(dy2, w2, b_major=MN_MAJOR, aux=pre, epi=EPI_DGELU)
         dw2 = _write_or_return_grad(
             w2, lambda dst, acc: gemm(dy2, act, a_major=MN_MAJOR, b_major=MN_MAJOR, out=dst, accumulate=acc))
-        db2 = _write_or_return_grad(b2, lambda dst, acc: colsum(dy2, dst, accumulate=acc))
+        db2 = None
+        if not _take_norm_colsum(b2):
+            db2 = _write_or_return_grad(b2, lambda dst, acc: colsum(dy2, dst, accumulate=acc))
         dx = gemm(dpre, w1, b_major=MN_MAJOR).view(ctx.xshape)
         dw1 = _write_or_return_grad(
             w1, lambda dst, acc: gemm(dpre, x2, a_major=MN_MAJOR, b_major=MN_MAJOR, out=dst, accumulate=acc))

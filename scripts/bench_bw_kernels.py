@@ -34,6 +34,14 @@ y, mean, rstd = F.layer_norm_fwd(x, w, b)
 dy = torch.randn_like(x)
 dg, db = torch.zeros(C, device=dev, dtype=torch.bfloat16), torch.zeros(C, device=dev, dtype=torch.bfloat16)
 report("layer_norm bwd [65536 x 768]", timeit(lambda: F.layer_norm_bwd(dy, x, w, mean, rstd, dg, db), flush), 3 * M * C * 2)
+rg = torch.randn_like(x)
+dcol = torch.zeros(C, device=dev, dtype=torch.bfloat16)
+report("layer_norm bwd + residual grad [65536 x 768]",
+       timeit(lambda: F.layer_norm_bwd(dy, x, w, mean, rstd, dg, db, res_grad=rg), flush), 4 * M * C * 2)
+report("layer_norm bwd + residual + dx column sums",
+       timeit(lambda: F.layer_norm_bwd(dy, x, w, mean, rstd, dg, db, res_grad=rg, dcol=dcol), flush), 4 * M * C * 2)
+if os.environ.get("BW_ONLY_NORM"):
+    sys.exit(0)
 for n in (768, 3072):
     d = torch.randn(M, n, device=dev).to(torch.bfloat16)
     out = torch.zeros(n, device=dev, dtype=torch.bfloat16)

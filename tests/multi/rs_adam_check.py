@@ -69,9 +69,11 @@ def main():
         dist.barrier()
 
     # CUDA-graph replay: device-side epoch/step counters must keep the ranks in lock-step
+    # (MAGGY_CHECK_GRAPH=0: eager, for compute-sanitizer runs — stream capture fails under the tool)
     from maggy_b200.parallel.trainer import build_gpt2_trainer
 
-    model, flat, opt, step = build_gpt2_trainer(cfg, 2, 64, dev, world_size=world, rank=rank, use_cuda_graph=True)
+    use_graph = os.environ.get("MAGGY_CHECK_GRAPH", "1") != "0"
+    model, flat, opt, step = build_gpt2_trainer(cfg, 2, 64, dev, world_size=world, rank=rank, use_cuda_graph=use_graph)
     idx = torch.randint(0, cfg.vocab_size, (2, 64)).pin_memory()
     tgt = torch.randint(0, cfg.vocab_size, (2, 64)).pin_memory()
     losses = [step(idx, tgt).item() for _ in range(8)]

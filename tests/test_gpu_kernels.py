@@ -435,3 +435,83 @@ def test_layer_norm_residual_gradient_is_folded_into_backward():
     ref.backward(g.float())
     assert ((y1.float() - ref).norm() / ref.norm()).item() < 1e-2
     assert ((gx1.float() - x2.grad).norm() / x2.grad.norm()).item() < 1.5e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,C", [(5000, 768), (4099, 1024), (300, 256), (513, 2048)])
+@pytest.mark.parametrize("rms", [False, True])
+@pytest.mark.parametrize("res", [False, True])
+def test_norm_bwd_staged_with_residual_and_column_sums(rows, C, rms, res):
+    """The bulk-copy staged norm backward (csrc/ops/norm.cu norm_bwd_kernel_v4): many rows per warp so the slot ring
+    wraps several times, optional residual gradient, and the column sums of dx (the producer's bias gradient) from
+    the same pass; C = 2048 takes the register-staged path plus a separate column-sum pass."""
+    from maggy_b200.ops import functional as F
+
+    torch.manual_seed(11)
+    x = torch.randn(rows, C, device="cuda", dtype=torch.bfloat16) * 1.5 + 0.3
+    w = (torch.randn(C, device="cuda") * 0.5 + 1).to(torch.bfloat16)
+    b = (torch.randn(C, device="cuda") * 0.1).to(torch.bfloat16)
+    dy = torch.randn(rows, C, device="cuda", dtype=torch.bfloat16)
+    rg = torch.randn(rows, C, device="cuda", dtype=torch.bfloat16) if res else None
+    xr, wr, br = x.float().requires_grad_(True), w.float().requires_grad_(True), b.float().requires_grad_(True)
+    if rms:
+        ref = xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-5) * wr
+    else:
+        ref = torch.nn.functional.layer_norm(xr, (C,), wr, br, 1e-5)
+    ref.backward(dy.float())
+    dx_ref = xr.grad + (rg.float() if res else 0)
+    _, mean, rstd = F.layer_norm_fwd(x, w, None if rms else b, 1e-5, rms)
+    dg, db = torch.empty_like(w), torch.empty_like(b)
+    dcol = torch.full((C,), 3.0, device="cuda", dtype=torch.bfloat16)
+    dx = F.layer_norm_bwd(dy, x, w, mean, rstd, dg, None if rms else db, rms=rms, res_grad=rg, dcol=dcol,
+                          accumulate_col=True)
+    rel = lambda a, r: ((a.float() - r.float()).norm() / r.float().norm()).item()
+    assert rel(dx, dx_ref) < 1e-2
+    assert rel(dg, wr.grad) < 1.5e-2
+    if not rms:
+        assert rel(db, br.grad) < 1.5e-2
+    assert rel(dcol, dx.float().sum(0) + 3.0) < 1e-2
+    # without the column sums / accumulate flag: same dx, dgamma accumulates
+    dg2 = dg.clone()
+    dx2 = F.layer_norm_bwd(dy, x, w, mean, rstd, dg2, None if rms else db, rms=rms, res_grad=rg, accumulate=True)
+    assert torch.equal(dx2, dx)
+    assert rel(dg2, 2 * wr.grad) < 2e-2
+
+
+@pytest.mark.gpu
+def test_bias_gradient_comes_out_of_the_following_norm():
+    """layer_norm(..., col_bias=b): the producing linear / mlp skips its column-sum pass and the bias gradient equals
+    the unfused one, with and without the main_grad arena convention."""
+    from maggy_b200.ops import functional as F
+
+    torch.manual_seed(5)
+    C, M = 768, 2048
+    mk = lambda *s, sc=1.0: (torch.randn(*s, device="cuda") * sc).to(torch.bfloat16)
+    x0, g = mk(M, C), mk(M, C)
+    params = [mk(C, C, sc=0.04), mk(C, sc=0.1), (1 + mk(C, sc=0.1)), mk(C, sc=0.1), mk(4 * C, C, sc=0.04), mk(4 * C, sc=0.1),
+              mk(C, 4 * C, sc=0.02), mk(C, sc=0.1)]
+
+    def run(fused: bool, main_grad: bool):
+        ps = [p.clone().requires_grad_(True) for p in params]
+        lw, lb, nw, nb, w1, b1, w2, b2 = ps
+        if main_grad:
+            for p in ps:
+                p.main_grad = torch.zeros_like(p)
+                p._mg_written = False
+        x = x0.clone().requires_grad_(True)
+        y = F.linear(x, lw, lb, residual=x)                                 # producer 1: linear with bias
+        h, y_res = F.layer_norm(y, nw, nb, 1e-5, with_residual=True, col_bias=lb if fused else None)
+        z = F.mlp(h, w1, b1, w2, b2, residual=y_res)                        # producer 2: mlp (fc2 bias)
+        out = F.layer_norm(z, nw, nb, 1e-5, col_bias=b2 if fused else None)
+        before = F.launch_count()
+        out.backward(g)
+        launches = F.launch_count() - before
+        grads = [(p.main_grad if main_grad else p.grad).float().clone() for p in ps]
+        return grads, x.grad.float().clone(), launches
+
+    for main_grad in (False, True):
+        (ref, gx_ref, n_ref), (got, gx, n_got) = run(False, main_grad), run(True, main_grad)
+        assert n_got == n_ref - 4, (n_got, n_ref)   # two colsum passes (partial + finalize each) are gone
+        assert torch.equal(gx, gx_ref)
+        for name, a, r in zip(["lw", "lb", "nw", "nb", "w1", "b1", "w2", "b2"], got, ref):
+            assert ((a - r).norm() / (r.norm() + 1e-6)).item() < 1e-2, (name, main_grad)
