@@ -11,7 +11,8 @@ Three routes, all on hand-written kernels:
   filter), wgrad is a pixel-reduction GEMM with both operands loaded as shifted 4-D TMA boxes;
 * **1x1, stride 1**: the activation tensor *is* the GEMM operand — ``ops.functional.linear`` on ``[N*H*W, C]``;
 * **explicit** (strided or thin-channel convolutions, e.g. the 7x7/2 stem): ``im2col`` gather kernel -> tcgen05
-  GEMM, backward ``col2im`` gather-sum; the column matrix is recomputed in backward instead of being saved.
+  GEMM, backward ``col2im`` gather-sum; the column matrix is kept for the wgrad GEMM (``MAGGY_B200_CONV_SAVE_COLS=0``
+  recomputes it instead). Thin-channel inputs use a shared-memory staged gather that writes whole 16-byte vectors.
 """
 from __future__ import annotations
 
@@ -25,6 +26,7 @@ from . import functional as F
 
 _P = _lib.c_void_p
 _I = _lib.c_int
+_SAVE_COLS = __import__("os").environ.get("MAGGY_B200_CONV_SAVE_COLS", "1") != "0"
 
 
 def _register():
@@ -142,6 +144,7 @@ class _Conv2d(torch.autograd.Function):
         assert x.shape[3] == C and weight2d.is_contiguous()
         weight = weight2d.view(Kout, R, S, C)
         ctx.R, ctx.S = R, S
+        ctx.cols = None
         ctx.stride, ctx.padding = stride, _pair(padding)
         ctx.pointwise = R == 1 and S == 1 and stride == 1 and ctx.padding == (0, 0)
         ctx.implicit = implicit_ok(C, Kout, stride)
@@ -158,6 +161,9 @@ class _Conv2d(torch.autograd.Function):
         P = (H + 2 * ctx.padding[0] - R) // stride + 1
         Q = (W + 2 * ctx.padding[1] - S) // stride + 1
         y = F.gemm(cols, _padded_filter(weight, cols.shape[1]))
+        # the column matrix is the wgrad operand: keep it (default; 244 MB for the ResNet-50 stem at batch 64) instead of
+        # gathering it a second time in backward. MAGGY_B200_CONV_SAVE_COLS=0 trades the memory back for the recompute.
+        ctx.cols = cols if _SAVE_COLS and ctx.needs_input_grad[1] else None
         return y.view(N, P, Q, Kout)
 
     @staticmethod
@@ -191,7 +197,8 @@ class _Conv2d(torch.autograd.Function):
                 else:
                     dst.copy_(dw32)
         else:
-            cols = im2col(x, R, S, ctx.stride, ctx.padding)  # recomputed, never saved
+            cols = ctx.cols if ctx.cols is not None else im2col(x, R, S, ctx.stride, ctx.padding)
+            ctx.cols = None
             dy2 = dy.view(-1, Kout)
             if ctx.needs_input_grad[0]:
                 dcols = F.gemm(dy2, _padded_filter(weight, cols.shape[1]), b_major=F.MN_MAJOR)

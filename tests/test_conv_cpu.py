@@ -77,3 +77,17 @@ def test_reference_imports_with_the_stand_ins():
         "print('REF_OK', r)\n" % (os.path.join(ROOT, "baseline"), ref_dir))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "REF_OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
+
+
+def test_fused_batchnorm_module_falls_back_on_cpu():
+    """ops.batchnorm.BatchNorm2d on CPU tensors = relu(batch_norm(x) + residual) through ATen (same state_dict keys)."""
+    import torch
+
+    from maggy_b200.ops.batchnorm import BatchNorm2d
+
+    torch.manual_seed(0)
+    bn, ref = BatchNorm2d(8, relu=True), torch.nn.BatchNorm2d(8)
+    assert set(bn.state_dict()) == set(ref.state_dict())
+    x, r = torch.randn(4, 8, 5, 5), torch.randn(4, 8, 5, 5)
+    assert torch.allclose(bn(x, r), torch.relu(ref(x) + r), atol=1e-6)
+    assert torch.allclose(bn.running_var, ref.running_var)

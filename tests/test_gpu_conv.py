@@ -68,6 +68,8 @@ def test_conv_wgrad_implicit(shape, splits):
     (2, 15, 15, 32, 64, 1, 2, 0),      # explicit 1x1 / 2
     (2, 32, 32, 3, 64, 7, 2, 3),       # explicit stem (C = 3)
     (2, 10, 10, 16, 24, 3, 1, 1),      # explicit (thin channels)
+    (2, 80, 72, 3, 64, 7, 2, 3),       # stem, Q = 36: one full and one partial tile of the staged thin-channel gather
+    (1, 20, 70, 5, 16, 3, 1, 1),       # C = 5, stride 1, three tiles per output row
 ])
 def test_conv_module_fwd_bwd(cfg):
     from maggy_b200.ops.conv import Conv2d
@@ -94,6 +96,9 @@ def test_conv_module_fwd_bwd(cfg):
 
 
 def test_resnet_native_vs_torch():
+    """Native convolutions + fused norms / pooling against the cuDNN + ATen model with the same weights. Both run in
+    bf16 and a deep stack of batch-norms over a batch of 8 amplifies rounding, so each is judged against the SAME model
+    evaluated in fp32: the native path may not be further from it than the stock bf16 path (plus a margin)."""
     from maggy_b200.models.resnet import ResNet
 
     torch.manual_seed(3)
@@ -109,20 +114,29 @@ def test_resnet_native_vs_torch():
             mod.load_state_dict(nsd[name].state_dict())
     x = torch.randn(8, 3, 64, 64, device="cuda").to(memory_format=torch.channels_last)
     y = torch.randint(0, 10, (8,), device="cuda")
+    l32 = torch.nn.functional.cross_entropy(ref(x), y)          # fp32 oracle
+    l32.backward()
+    g32 = {n: p.grad.clone() for n, p in ref.named_parameters()}
+    ref.zero_grad(set_to_none=True)
     with torch.autocast("cuda", dtype=torch.bfloat16):
         l1 = torch.nn.functional.cross_entropy(native(x), y)
         l2 = torch.nn.functional.cross_entropy(ref(x), y)
     l1.backward()
     l2.backward()
-    assert abs(l1.item() - l2.item()) < 5e-2 * max(1.0, abs(l2.item()))
+    assert abs(l1.item() - l32.item()) < 5e-2 * max(1.0, abs(l32.item()))
     g1 = native.layer1[0].conv2.weight.grad.view(64, 3, 3, 64).permute(0, 3, 1, 2)
-    g2 = ref.layer1[0].conv2.weight.grad
-    assert _rel(g1, g2) < 0.1
+    e_native = _rel(g1, g32["layer1.0.conv2.weight"])
+    e_stock = _rel(ref.layer1[0].conv2.weight.grad, g32["layer1.0.conv2.weight"])
+    assert e_native < max(0.05, 1.5 * e_stock), (e_native, e_stock)
+    e_native = _rel(native.layer4[0].bn3.weight.grad, g32["layer4.0.bn3.weight"])
+    e_stock = _rel(ref.layer4[0].bn3.weight.grad, g32["layer4.0.bn3.weight"])
+    assert e_native < max(0.05, 1.5 * e_stock), (e_native, e_stock)
     assert torch.isfinite(native.conv1.weight.grad.float()).all()
 
 
 def test_resnet_trainstep_graph():
-    """Whole ResNet step (native convs, ATen BatchNorm adopted into the arena, fused AdamW) replayed as a CUDA graph."""
+    """Whole ResNet step (native convs, fused norms writing straight into the arena, the ATen classifier head adopted
+    into it, fused AdamW) replayed as a CUDA graph."""
     from maggy_b200.models.resnet import ResNet
     from maggy_b200.parallel.trainer import build_trainer
 
@@ -142,5 +156,7 @@ def test_resnet_trainstep_graph():
     assert all(l == l for l in losses)
     assert losses[-1] < losses[0] * 0.7, losses
     assert step.graph is not None and len(flat._autograd_ranges) >= 1
-    bn = model.bn1.weight
-    assert bn.grad is not None and bn.grad.data_ptr() == bn.main_grad.data_ptr()
+    fc = model.fc.weight   # nn.Linear: gradient produced by ATen autograd, adopted into the arena
+    assert fc.grad is not None and fc.grad.data_ptr() == fc.main_grad.data_ptr()
+    bn = model.bn1.weight  # fused norm: written by the kernel into the arena, no autograd .grad
+    assert bn.grad is None and float(bn.main_grad.float().abs().sum()) > 0
