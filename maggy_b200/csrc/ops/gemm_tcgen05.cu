@@ -731,23 +731,30 @@ extern "C" int mg_gemm_auto_splits(int M, int N, int K, int block_n) {
   int sms = num_sms() > 0 ? num_sms() : 148;
   if (tiles * 2 > sms || kb < 32) return 1;
   // Work units are scheduled on CTA pairs for 256-wide tiles (one unit = two vertically adjacent tiles), on single
-  // CTAs otherwise. Pick the split count that fills whole waves best: e.g. the qkv weight gradient (18 x 3 tiles)
-  // gets 5 splits = 135 pair units = 1.82 waves (91 % busy) instead of 2 splits = 54 units (73 %). Each extra split
-  // costs one more fp32 partial of the output, hence the mild penalty; >= 16 k-blocks (1024 of K) per split.
+  // CTAs otherwise. Model, in SM cycles:  T(sp) = waves(sp) * ceil(kb / sp) * t_kb  +  reduce(sp)
+  //   t_kb      one k-block of one tile on the tensor pipe (8192 dense bf16 FLOP/clk/SM): 2 * block_n cycles
+  //   reduce    second pass over sp fp32 partials of the output (~3.4 KB/clk of HBM at 6.5 TB/s) + one launch
+  // e.g. the GPT-2 qkv weight gradient (18 x 3 tiles, kb = 512..1024) gets 5 splits = 135 pair units = 1.82 waves
+  // (91 % busy) instead of 2 splits = 54 units (73 %); the ResNet stem / layer-1 weight gradients (1-8 tiles, K = 200 k
+  // ... 800 k pixels) get one split per SM — the 16-split cap of round 1 ran them on 16-32 SMs at 0.2x of the HBM
+  // bound (profiles/resnet_r2/). At least 8 k-blocks (512 of K) per split.
   const bool pairs = block_n == 256 && m_blocks >= 2;
   const long long units1 = pairs ? ((m_blocks + 1) / 2) * n_blocks : tiles;
   const long long slots = pairs ? sms / 2 : sms;
-  int max_s = kb / 16;
-  if (max_s > 16) max_s = 16;
+  long long max_s = kb / 8;
+  if (max_s > slots) max_s = slots;
+  const double t_kb = 2.0 * block_n;
+  const double out_bytes = 8.0 * static_cast<double>(M) * static_cast<double>(N);  // one fp32 partial: write + read
   int best = 1;
-  double best_score = 0.0;
+  double best_t = 0.0;
   for (int sp = 1; sp <= max_s; ++sp) {
     const long long units = units1 * sp;
     const long long waves = (units + slots - 1) / slots;
-    // time ~ waves * (K / sp): maximise sp / waves
-    const double score = static_cast<double>(sp) / static_cast<double>(waves) - 0.02 * sp;
-    if (score > best_score + 1e-9) {
-      best_score = score;
+    const long long kbs = (kb + sp - 1) / sp;
+    double t = static_cast<double>(waves) * static_cast<double>(kbs) * t_kb;
+    if (sp > 1) t += 4000.0 + sp * out_bytes / 3400.0;
+    if (sp == 1 || t < best_t * 0.97) {  // a further split has to buy at least 3 %
+      best_t = t;
       best = sp;
     }
   }

@@ -53,11 +53,15 @@ class Bottleneck(nn.Module):
         self.downsample = downsample
 
     def forward(self, x):
-        idt = x if self.downsample is None else self.downsample(x)
         if self.fused:
-            out = self.bn1(self.conv1(x))            # norm + ReLU in one kernel
+            # x_skip aliases x: the skip / downsample gradient comes back through conv1's backward and is added in its
+            # dgrad epilogue instead of by an autograd add kernel
+            out, x_skip = self.conv1(x, with_skip=True)
+            idt = x_skip if self.downsample is None else self.downsample(x_skip)
+            out = self.bn1(out)                      # norm + ReLU in one kernel
             out = self.bn2(self.conv2(out))
             return self.bn3(self.conv3(out), idt)    # norm + skip add + ReLU in one kernel
+        idt = x if self.downsample is None else self.downsample(x)
         out = self.relu(self.bn1(self.conv1(x)))
         out = self.relu(self.bn2(self.conv2(out)))
         out = self.bn3(self.conv3(out))

@@ -136,9 +136,17 @@ class _Conv2d(torch.autograd.Function):
     """x: [N,H,W,C] bf16, weight2d: [Kout, R*S*C] bf16 (KRSC flattened) -> [N,P,Q,Kout] bf16."""
 
     @staticmethod
-    def forward(ctx, x, weight2d, R, S, stride, padding):
+    def forward(ctx, x, weight2d, R, S, stride, padding, with_skip=False):
         if not x.is_contiguous():
             x = x.contiguous()
+        ctx.with_skip = with_skip
+        y = _Conv2d._forward(ctx, x, weight2d, R, S, stride, padding)
+        # with_skip: also hand back x itself (an alias, no kernel) for the skip connection around this convolution, so
+        # the skip gradient arrives in THIS backward and is added in the dgrad GEMM epilogue (no separate add kernel)
+        return (y, x.view_as(x)) if with_skip else y
+
+    @staticmethod
+    def _forward(ctx, x, weight2d, R, S, stride, padding):
         Kout = weight2d.shape[0]
         C = weight2d.shape[1] // (R * S)
         assert x.shape[3] == C and weight2d.is_contiguous()
@@ -167,22 +175,30 @@ class _Conv2d(torch.autograd.Function):
         return y.view(N, P, Q, Kout)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dskip=None):
         x, weight2d = ctx.saved_tensors
         R, S = ctx.R, ctx.S
         Kout, C = weight2d.shape[0], weight2d.shape[1] // (R * S)
         weight = weight2d.view(Kout, R, S, C)
+        if dy is None:  # only the skip connection carried a gradient
+            return dskip, None, None, None, None, None, None
         if not dy.is_contiguous():
             dy = dy.contiguous()
+        if dskip is not None and not dskip.is_contiguous():
+            dskip = dskip.contiguous()
         dx = None
         if ctx.pointwise:
             dy2, x2 = dy.view(-1, Kout), x.view(-1, C)
             if ctx.needs_input_grad[0]:
-                dx = F.gemm(dy2, weight.view(Kout, C), b_major=F.MN_MAJOR).view(x.shape)
+                if dskip is not None:   # dx = dY W + dskip in one epilogue
+                    dx = F.gemm(dy2, weight.view(Kout, C), b_major=F.MN_MAJOR, aux=dskip.view(-1, C),
+                                epi=F.EPI_BIAS_RESIDUAL).view(x.shape)
+                else:
+                    dx = F.gemm(dy2, weight.view(Kout, C), b_major=F.MN_MAJOR).view(x.shape)
             dw = F._write_or_return_grad(
                 ctx.weight_ref,
                 lambda dst, acc: F.gemm(dy2, x2, a_major=F.MN_MAJOR, b_major=F.MN_MAJOR, out=dst, accumulate=acc))
-            return dx, dw, None, None, None, None
+            return dx, dw, None, None, None, None, None
         if ctx.implicit:
             ph, pw = ctx.padding
             if ctx.needs_input_grad[0]:
@@ -213,19 +229,22 @@ class _Conv2d(torch.autograd.Function):
                 else:
                     dst.copy_(dw32)
         dw = F._write_or_return_grad(ctx.weight_ref, into)
-        return dx, dw, None, None, None, None
+        if dskip is not None:
+            dx = dskip if dx is None else dx + dskip
+        return dx, dw, None, None, None, None, None
 
 
-def conv2d(x: torch.Tensor, weight: torch.Tensor, stride: int = 1, padding=0, kernel_size=None) -> torch.Tensor:
+def conv2d(x: torch.Tensor, weight: torch.Tensor, stride: int = 1, padding=0, kernel_size=None, with_skip=False):
     """NHWC convolution: ``x`` [N,H,W,C] bf16, ``weight`` [Kout,R,S,C] (or [Kout, R*S*C] with ``kernel_size``) bf16
-    -> [N,P,Q,Kout] bf16."""
+    -> [N,P,Q,Kout] bf16. ``with_skip=True`` returns ``(y, x_skip)``: feed ``x_skip`` (an alias of ``x``) into the
+    skip connection around the convolution and its gradient is added inside the dgrad epilogue."""
     if weight.dim() == 4:
         Kout, R, S, C = weight.shape
         assert weight.is_contiguous(), "KRSC filter must be contiguous"
         weight = weight.view(Kout, R * S * C)
     else:
         R, S = _pair(kernel_size)
-    return _Conv2d.apply(x, weight, R, S, stride, padding)
+    return _Conv2d.apply(x, weight, R, S, stride, padding, with_skip)
 
 
 class Conv2d(torch.nn.Module):
@@ -261,12 +280,16 @@ class Conv2d(torch.nn.Module):
         kh, kw = self.kernel_size
         return self.weight.view(self.out_channels, kh, kw, self.in_channels).permute(0, 3, 1, 2)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, with_skip: bool = False):
         if not x.is_cuda:
-            return torch.nn.functional.conv2d(x, self.torch_weight().to(x.dtype), None, self.stride, self.padding)
+            y = torch.nn.functional.conv2d(x, self.torch_weight().to(x.dtype), None, self.stride, self.padding)
+            return (y, x) if with_skip else y
         xn = x.permute(0, 2, 3, 1)  # NHWC view of a channels_last tensor
         if xn.dtype != torch.bfloat16:
             xn = xn.to(torch.bfloat16)
+        if with_skip:
+            y, xs = conv2d(xn, self.weight, self.stride, self.padding, kernel_size=self.kernel_size, with_skip=True)
+            return y.permute(0, 3, 1, 2), xs.permute(0, 3, 1, 2)
         y = conv2d(xn, self.weight, self.stride, self.padding, kernel_size=self.kernel_size)
         return y.permute(0, 3, 1, 2)  # logical NCHW, channels_last memory
 

@@ -160,3 +160,27 @@ def test_resnet_trainstep_graph():
     assert fc.grad is not None and fc.grad.data_ptr() == fc.main_grad.data_ptr()
     bn = model.bn1.weight  # fused norm: written by the kernel into the arena, no autograd .grad
     assert bn.grad is None and float(bn.main_grad.float().abs().sum()) > 0
+
+
+@pytest.mark.parametrize("k,stride,pad", [(1, 1, 0), (3, 1, 1), (1, 2, 0)])
+def test_conv_with_skip_adds_the_skip_gradient_in_backward(k, stride, pad):
+    """Conv2d(x, with_skip=True) -> (y, x_skip): the gradient arriving through x_skip is added to dgrad (in the GEMM
+    epilogue for 1x1 convolutions) — same x.grad as the unfused graph where autograd adds the two."""
+    from maggy_b200.ops.conv import Conv2d
+
+    torch.manual_seed(5)
+    m = Conv2d(64, 128, k, stride=stride, padding=pad).cuda()
+    x = torch.randn(4, 64, 16, 16, device="cuda").to(torch.bfloat16).to(memory_format=torch.channels_last)
+    x1, x2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    y1, xs = m(x1, with_skip=True)
+    gy, gs = torch.randn_like(y1), torch.randn_like(x)
+    (y1 * gy).sum().backward(retain_graph=True)
+    only_conv = x1.grad.clone()
+    x1.grad = None
+    m.weight.grad = None
+    ((y1 * gy).sum() + (xs * gs).sum()).backward()
+    y2 = m(x2)
+    ((y2 * gy).sum() + (x2 * gs).sum()).backward()
+    assert torch.equal(y1, y2)
+    assert _rel(x1.grad, x2.grad) < 1e-2
+    assert _rel(x1.grad.float() - only_conv.float(), gs) < 2e-2

@@ -515,3 +515,23 @@ def test_bias_gradient_comes_out_of_the_following_norm():
         assert torch.equal(gx, gx_ref)
         for name, a, r in zip(["lw", "lb", "nw", "nb", "w1", "b1", "w2", "b2"], got, ref):
             assert ((a - r).norm() / (r.norm() + 1e-6)).item() < 1e-2, (name, main_grad)
+
+
+@pytest.mark.gpu
+def test_pair_gemm_is_deterministic():
+    """The CTA-pair (cta_group::2) GEMM path that serves the big training shapes: 20 launches on the same operands are
+    bit-identical, for the K-major forward and the MN-major dgrad / wgrad forms (compute-sanitizer racecheck cannot follow
+    the cluster-scope mbarrier that orders the peer CTA's multicast against the MMA reads: profiles/sanitizer_r2.md)."""
+    from maggy_b200.ops import functional as F
+
+    torch.manual_seed(9)
+    M, N, K = 8192, 3072, 768
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+    dy = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+    forms = [lambda: F.gemm(a, b), lambda: F.gemm(dy, b, b_major=F.MN_MAJOR),
+             lambda: F.gemm(dy, a, a_major=F.MN_MAJOR, b_major=F.MN_MAJOR, splits=1)]
+    for f in forms:
+        first = f().clone()
+        for _ in range(20):
+            assert torch.equal(f(), first)
