@@ -73,6 +73,7 @@ __device__ __forceinline__ void block_fold(float (&acc)[NACC][8], int V, int C, 
 
 __global__ void __launch_bounds__(512)
 bn_stats_kernel(const uint4* __restrict__ x, long long total, int V, int C, float* __restrict__ partial) {
+  pdl_prologue();
   extern __shared__ float red[];
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -128,6 +129,7 @@ bn_fwd_finalize_kernel(const float* __restrict__ partial, int nparts, int C, dou
                        const void* __restrict__ gamma, const void* __restrict__ beta, int param_bf16,
                        float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps,
                        float* __restrict__ stats, float* __restrict__ coef, long long* __restrict__ num_batches) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   float s = 0.f, q = 0.f;
@@ -179,6 +181,7 @@ bn_fwd_finalize_kernel(const float* __restrict__ partial, int nparts, int C, dou
 __global__ void bn_eval_coef_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                     const void* __restrict__ gamma, const void* __restrict__ beta, int param_bf16,
                                     float eps, int C, float* __restrict__ coef) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float invstd = rsqrtf(running_var[c] + eps);
@@ -192,6 +195,7 @@ template <bool RELU, bool RES>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res, uint4* __restrict__ y,
                 const float* __restrict__ coef, long long total, int V, int C) {
+  pdl_prologue();
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int v = static_cast<int>(i % V);
@@ -234,6 +238,7 @@ template <bool RELU>
 __global__ void __launch_bounds__(512)
 bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, const uint4* __restrict__ x,
                      const float* __restrict__ stats, long long total, int V, int C, float* __restrict__ partial) {
+  pdl_prologue();
   extern __shared__ float red[];
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -283,6 +288,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int nparts, int C, flo
                        const void* __restrict__ gamma, int param_bf16, const float* __restrict__ stats,
                        void* __restrict__ dgamma, void* __restrict__ dbeta, int accumulate,
                        float* __restrict__ coef /* [3][C] */) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   float s = 0.f, q = 0.f;
@@ -330,6 +336,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_elemt_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, const uint4* __restrict__ x,
                     const float* __restrict__ coef, uint4* __restrict__ dx, uint4* __restrict__ dz_out,
                     long long total, int V, int C) {
+  pdl_prologue();
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int v = static_cast<int>(i % V);
@@ -405,11 +412,11 @@ extern "C" int mg_bn_fwd_stats(const void* x, long long M, int C, const void* ga
   const int V = C / 8;
   const long long total = M * V;
   const Geom g = geom(total, V, kPartThreads, 8, kPartCap);
-  bn_stats_kernel<<<g.grid, g.threads, g.threads * 17 * sizeof(float), s>>>(reinterpret_cast<const uint4*>(x), total, V, C,
+  launch_pdl(bn_stats_kernel, dim3(g.grid), dim3(g.threads), g.threads * 17 * sizeof(float), s, 1, reinterpret_cast<const uint4*>(x), total, V, C,
                                                                           partial);
   const double inv_m = 1.0 / static_cast<double>(M);
   const double unbias = M > 1 ? static_cast<double>(M) / static_cast<double>(M - 1) : 1.0;
-  bn_fwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(partial, g.grid, C, inv_m, unbias, gamma, beta, param_bf16,
+  launch_pdl(bn_fwd_finalize_kernel, dim3((C + 31) / 32), dim3(1024), 0, s, 1, partial, g.grid, C, inv_m, unbias, gamma, beta, param_bf16,
                                                        running_mean, running_var, momentum, eps, stats, coef,
                                                        num_batches);
   return check();
@@ -418,7 +425,7 @@ extern "C" int mg_bn_fwd_stats(const void* x, long long M, int C, const void* ga
 extern "C" int mg_bn_eval_coef(const float* running_mean, const float* running_var, const void* gamma,
                                const void* beta, int param_bf16, float eps, int C, float* coef, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  bn_eval_coef_kernel<<<(C + 127) / 128, 128, 0, s>>>(running_mean, running_var, gamma, beta, param_bf16, eps, C, coef);
+  launch_pdl(bn_eval_coef_kernel, dim3((C + 127) / 128), dim3(128), 0, s, 1, running_mean, running_var, gamma, beta, param_bf16, eps, C, coef);
   return check();
 }
 
@@ -433,11 +440,11 @@ extern "C" int mg_bn_apply(const void* x, const void* res, void* y, const float*
   const uint4 *xp = reinterpret_cast<const uint4*>(x), *rp = reinterpret_cast<const uint4*>(res);
   uint4* yp = reinterpret_cast<uint4*>(y);
   if (relu) {
-    if (res) bn_apply_kernel<true, true><<<g.grid, g.threads, 0, s>>>(xp, rp, yp, coef, total, V, C);
-    else bn_apply_kernel<true, false><<<g.grid, g.threads, 0, s>>>(xp, rp, yp, coef, total, V, C);
+    if (res) launch_pdl(bn_apply_kernel<true, true>, dim3(g.grid), dim3(g.threads), 0, s, 1, xp, rp, yp, coef, total, V, C);
+    else launch_pdl(bn_apply_kernel<true, false>, dim3(g.grid), dim3(g.threads), 0, s, 1, xp, rp, yp, coef, total, V, C);
   } else {
-    if (res) bn_apply_kernel<false, true><<<g.grid, g.threads, 0, s>>>(xp, rp, yp, coef, total, V, C);
-    else bn_apply_kernel<false, false><<<g.grid, g.threads, 0, s>>>(xp, rp, yp, coef, total, V, C);
+    if (res) launch_pdl(bn_apply_kernel<false, true>, dim3(g.grid), dim3(g.threads), 0, s, 1, xp, rp, yp, coef, total, V, C);
+    else launch_pdl(bn_apply_kernel<false, false>, dim3(g.grid), dim3(g.threads), 0, s, 1, xp, rp, yp, coef, total, V, C);
   }
   return check();
 }
@@ -455,18 +462,18 @@ extern "C" int mg_bn_bwd(const void* dy, const void* y, const void* x, const flo
               *xp = reinterpret_cast<const uint4*>(x);
   const Geom g = geom(total, V, kPartThreads, 8, kPartCap);
   const size_t smem = g.threads * 17 * sizeof(float);
-  if (relu) bn_bwd_reduce_kernel<true><<<g.grid, g.threads, smem, s>>>(dyp, yp, xp, stats, total, V, C, partial);
-  else bn_bwd_reduce_kernel<false><<<g.grid, g.threads, smem, s>>>(dyp, yp, xp, stats, total, V, C, partial);
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(partial, g.grid, C, 1.0f / static_cast<float>(M), gamma,
+  if (relu) launch_pdl(bn_bwd_reduce_kernel<true>, dim3(g.grid), dim3(g.threads), smem, s, 1, dyp, yp, xp, stats, total, V, C, partial);
+  else launch_pdl(bn_bwd_reduce_kernel<false>, dim3(g.grid), dim3(g.threads), smem, s, 1, dyp, yp, xp, stats, total, V, C, partial);
+  launch_pdl(bn_bwd_finalize_kernel, dim3((C + 31) / 32), dim3(1024), 0, s, 1, partial, g.grid, C, 1.0f / static_cast<float>(M), gamma,
                                                        param_bf16, stats, dgamma, dbeta, accumulate, coef);
   const Geom e = geom(total, V, 256, 8, kElemCap);
   uint4 *dxp = reinterpret_cast<uint4*>(dx), *dzp = reinterpret_cast<uint4*>(dz);
   if (relu) {
-    if (dz) bn_bwd_elemt_kernel<true, true><<<e.grid, e.threads, 0, s>>>(dyp, yp, xp, coef, dxp, dzp, total, V, C);
-    else bn_bwd_elemt_kernel<true, false><<<e.grid, e.threads, 0, s>>>(dyp, yp, xp, coef, dxp, dzp, total, V, C);
+    if (dz) launch_pdl(bn_bwd_elemt_kernel<true, true>, dim3(e.grid), dim3(e.threads), 0, s, 1, dyp, yp, xp, coef, dxp, dzp, total, V, C);
+    else launch_pdl(bn_bwd_elemt_kernel<true, false>, dim3(e.grid), dim3(e.threads), 0, s, 1, dyp, yp, xp, coef, dxp, dzp, total, V, C);
   } else {
-    if (dz) bn_bwd_elemt_kernel<false, true><<<e.grid, e.threads, 0, s>>>(dyp, yp, xp, coef, dxp, dzp, total, V, C);
-    else bn_bwd_elemt_kernel<false, false><<<e.grid, e.threads, 0, s>>>(dyp, yp, xp, coef, dxp, dzp, total, V, C);
+    if (dz) launch_pdl(bn_bwd_elemt_kernel<false, true>, dim3(e.grid), dim3(e.threads), 0, s, 1, dyp, yp, xp, coef, dxp, dzp, total, V, C);
+    else launch_pdl(bn_bwd_elemt_kernel<false, false>, dim3(e.grid), dim3(e.threads), 0, s, 1, dyp, yp, xp, coef, dxp, dzp, total, V, C);
   }
   return check();
 }

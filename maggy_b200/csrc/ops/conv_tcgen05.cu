@@ -76,6 +76,7 @@ template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv2d_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w,
                             const __grid_constant__ CUtensorMap tma_y, const ConvParams p) {
+  pdl_launch_dependents();
   using L = FpropSmem<BLOCK_N, STAGES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -116,6 +117,7 @@ conv2d_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_x, const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp_idx == 0) {
     // ============================ TMA producer ============================
@@ -269,6 +271,7 @@ template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv2d_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_constant__ CUtensorMap tma_x,
                             const ConvParams p) {
+  pdl_launch_dependents();
   using L = WgradSmem<BLOCK_N, STAGES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -319,6 +322,7 @@ conv2d_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_dy, const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp_idx == 0) {
     if (lane == 0) {
@@ -452,6 +456,7 @@ template <int VEC>
 __global__ void im2col_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ cols, int N,
                                    int H, int W, int C, int R, int S, int P, int Q, int stride, int pad_h, int pad_w,
                                    int Kp) {
+  pdl_prologue();
   const long long vec_per_row = Kp / VEC;
   const long long total = static_cast<long long>(N) * P * Q * vec_per_row;
   const int RSC = R * S * C;
@@ -495,6 +500,7 @@ constexpr int kTileQ = 32;
 __global__ void __launch_bounds__(256)
 im2col_thin_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ cols, int N, int H, int W, int C,
                    int R, int S, int P, int Q, int stride, int pad_h, int pad_w, int Kp) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int span = ((kTileQ - 1) * stride + S) * C;  // patch row length in elements
   short* off = reinterpret_cast<short*>(smem_raw);                                        // [Kp]
@@ -547,6 +553,7 @@ template <int VEC>
 __global__ void col2im_nhwc_kernel(const __nv_bfloat16* __restrict__ dcols, __nv_bfloat16* __restrict__ dx, int N,
                                    int H, int W, int C, int R, int S, int P, int Q, int stride, int pad_h, int pad_w,
                                    int Kp) {
+  pdl_prologue();
   const int cv = C / VEC;
   const long long total = static_cast<long long>(N) * H * W * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -699,8 +706,7 @@ int launch_fprop(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap
   }
   const int tiles = p.num_m_tiles * p.num_n_blocks;
   const int grid = tiles < max_ctas ? tiles : max_ctas;
-  kern<<<grid, kNumThreads, smem_bytes, stream>>>(mx, mw, my, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kNumThreads), smem_bytes, stream, 1, mx, mw, my, p);
   if (e != cudaSuccess) fprintf(stderr, "maggy_b200 conv fprop: launch failed: %s\n", cudaGetErrorString(e));
   return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
 }
@@ -720,8 +726,7 @@ int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const ConvParams
   }
   const int units = p.splits * p.R * p.S * ((p.Kout + BLOCK_M - 1) / BLOCK_M) * p.num_n_blocks;
   const int grid = units < max_ctas ? units : max_ctas;
-  kern<<<grid, kNumThreads, smem_bytes, stream>>>(mdy, mx, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kNumThreads), smem_bytes, stream, 1, mdy, mx, p);
   if (e != cudaSuccess) fprintf(stderr, "maggy_b200 conv wgrad: launch failed: %s\n", cudaGetErrorString(e));
   return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
 }
@@ -805,7 +810,7 @@ int mg_im2col_nhwc(const void* x, void* cols, int N, int H, int W, int C, int R,
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   if (vec)
-    im2col_nhwc_kernel<8><<<static_cast<int>(blocks), 256, 0, s>>>(
+    launch_pdl(im2col_nhwc_kernel<8>, dim3(static_cast<int>(blocks)), dim3(256), 0, s, 1, 
         static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(cols), N, H, W, C, R, S, P, Q, stride, pad_h,
         pad_w, Kp);
   else {
@@ -814,11 +819,11 @@ int mg_im2col_nhwc(const void* x, void* cols, int N, int H, int W, int C, int R,
     static const bool scalar = getenv("MAGGY_B200_IM2COL_SCALAR") != nullptr;  // the first kernel, for A/B runs
     if (!scalar && smem <= 48 * 1024 && R * ((kTileQ - 1) * stride + S) * C < 32768 && Kp % 8 == 0) {
       const int grid = static_cast<int>(tiles < 148LL * 8 ? tiles : 148LL * 8);
-      im2col_thin_kernel<<<grid, 256, smem, s>>>(static_cast<const __nv_bfloat16*>(x),
+      launch_pdl(im2col_thin_kernel, dim3(grid), dim3(256), smem, s, 1, static_cast<const __nv_bfloat16*>(x),
                                                  static_cast<__nv_bfloat16*>(cols), N, H, W, C, R, S, P, Q, stride,
                                                  pad_h, pad_w, Kp);
     } else {
-      im2col_nhwc_kernel<1><<<static_cast<int>(blocks), 256, 0, s>>>(
+      launch_pdl(im2col_nhwc_kernel<1>, dim3(static_cast<int>(blocks)), dim3(256), 0, s, 1, 
           static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(cols), N, H, W, C, R, S, P, Q, stride,
           pad_h, pad_w, Kp);
     }
@@ -838,11 +843,11 @@ int mg_col2im_nhwc(const void* dcols, void* dx, int N, int H, int W, int C, int 
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   if (vec)
-    col2im_nhwc_kernel<8><<<static_cast<int>(blocks), 256, 0, s>>>(
+    launch_pdl(col2im_nhwc_kernel<8>, dim3(static_cast<int>(blocks)), dim3(256), 0, s, 1, 
         static_cast<const __nv_bfloat16*>(dcols), static_cast<__nv_bfloat16*>(dx), N, H, W, C, R, S, P, Q, stride,
         pad_h, pad_w, Kp);
   else
-    col2im_nhwc_kernel<1><<<static_cast<int>(blocks), 256, 0, s>>>(
+    launch_pdl(col2im_nhwc_kernel<1>, dim3(static_cast<int>(blocks)), dim3(256), 0, s, 1, 
         static_cast<const __nv_bfloat16*>(dcols), static_cast<__nv_bfloat16*>(dx), N, H, W, C, R, S, P, Q, stride,
         pad_h, pad_w, Kp);
   cudaError_t e = cudaGetLastError();

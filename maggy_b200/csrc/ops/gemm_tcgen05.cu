@@ -110,6 +110,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                          const __grid_constant__ CUtensorMap tma_c,
                          const __grid_constant__ CUtensorMap tma_aux, const GemmParams p) {
   constexpr bool MC = MODE == 1, PAIR = MODE == 2, CL = MODE != 0;
+  pdl_launch_dependents();  // the next kernel may be scheduled behind this grid's last wave (see mg_ptx.cuh)
   constexpr int KB_ELEMS = FP8 ? 128 : BLOCK_K;  // elements per k-block (always 128 bytes)
   static_assert(!FP8 || (A_MAJOR == 0 && B_MAJOR == 0), "fp8 operands are K-major");
   using L = SmemLayout<(PAIR ? BLOCK_N / 2 : BLOCK_N), STAGES>;  // PAIR: each CTA stages half of the B tile
@@ -173,6 +174,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   if constexpr (CL) cluster_sync();  // peer barriers must be initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // barriers, TMEM and descriptors were set up under the predecessor's tail; its output is needed from here on
 
   if (warp_idx == 0) {
     // ============================ TMA producer ============================
@@ -532,34 +534,60 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   }
 }
 
-// out[i] (+)= sum_s ws[s][i]   (split-K second pass; n multiple of 4)
+// out[i] (+)= sum_s ws[s][i]   (split-K second pass; n multiple of 4). A CTA is 32 output vectors x 8 split lanes:
+// lane y sums splits y, y+8, ... (up to four loads in flight), the eight partial sums meet in shared memory. With one
+// split per SM (thin weight gradients: up to 148 partials) a single thread walking all the splits was a chain of
+// L2 latencies (12.6 us per launch in the ResNet step).
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long n, void* __restrict__ out,
                      int out_f32, int accumulate) {
+  pdl_prologue();
   const long long nvec = n >> 2;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float4 acc = reinterpret_cast<const float4*>(ws)[i];
-    for (int s = 1; s < splits; ++s) {
-      float4 t = reinterpret_cast<const float4*>(ws + s * n)[i];
-      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-    }
-    if (out_f32) {
-      float4* o = reinterpret_cast<float4*>(out) + i;
-      if (accumulate) {
-        float4 t = *o;
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  __shared__ float4 red[8][32];
+  for (long long i0 = static_cast<long long>(blockIdx.x) * 32; i0 < nvec; i0 += static_cast<long long>(gridDim.x) * 32) {
+    const long long i = i0 + x;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < nvec) {
+      int s = y;
+      for (; s + 24 < splits; s += 32) {
+        float4 t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[k] = reinterpret_cast<const float4*>(ws + static_cast<long long>(s + 8 * k) * n)[i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { acc.x += t[k].x; acc.y += t[k].y; acc.z += t[k].z; acc.w += t[k].w; }
+      }
+      for (; s < splits; s += 8) {
+        const float4 t = reinterpret_cast<const float4*>(ws + static_cast<long long>(s) * n)[i];
         acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
       }
-      *o = acc;
-    } else {
-      uint2* o = reinterpret_cast<uint2*>(out) + i;
-      if (accumulate) {
-        uint2 t = *o;
-        float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y);
-        acc.x += a.x; acc.y += a.y; acc.z += b.x; acc.w += b.y;
-      }
-      *o = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
     }
+    red[y][x] = acc;
+    __syncthreads();
+    if (y == 0 && i < nvec) {
+#pragma unroll
+      for (int k = 1; k < 8; ++k) {
+        const float4 t = red[k][x];
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+      if (out_f32) {
+        float4* o = reinterpret_cast<float4*>(out) + i;
+        if (accumulate) {
+          float4 t = *o;
+          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        *o = acc;
+      } else {
+        uint2* o = reinterpret_cast<uint2*>(out) + i;
+        if (accumulate) {
+          uint2 t = *o;
+          float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y);
+          acc.x += a.x; acc.y += a.y; acc.z += b.x; acc.w += b.y;
+        }
+        *o = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -649,26 +677,7 @@ int launch(const Maps& m, const GemmParams& p, int max_ctas, cudaStream_t stream
   cudaError_t stale = cudaGetLastError();  // do not blame this launch for an older, unchecked error
   if (stale != cudaSuccess)
     fprintf(stderr, "maggy_b200 gemm: clearing stale CUDA error before launch: %s\n", cudaGetErrorString(stale));
-  cudaError_t e;
-  if (MC) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kNumThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, m.a, m.b, m.c, m.aux, p);
-    if (e == cudaSuccess) e = cudaGetLastError();
-  } else {
-    kern<<<grid, kNumThreads, smem_bytes, stream>>>(m.a, m.b, m.c, m.aux, p);
-    e = cudaGetLastError();
-  }
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kNumThreads), smem_bytes, stream, MC ? 2 : 1, m.a, m.b, m.c, m.aux, p);
   if (e != cudaSuccess) {
     int dev = -1;
     cudaGetDevice(&dev);
@@ -843,10 +852,10 @@ extern "C" int mg_gemm_bf16(const void* A, const void* B, void* C, const void* b
   if (p.splits > 1) {
     long long n = static_cast<long long>(M) * N;
     long long nvec = n >> 2;
-    int grid = static_cast<int>((nvec + 255) / 256);
-    if (grid > 148 * 8) grid = 148 * 8;
-    splitk_reduce_kernel<<<grid, 256, 0, s>>>(ws, p.splits, n, C, out_f32, accumulate);
-    cudaError_t e = cudaGetLastError();
+    long long blocks = (nvec + 31) / 32;
+    int grid = static_cast<int>(blocks < 148LL * 32 ? blocks : 148LL * 32);
+    cudaError_t e = launch_pdl(splitk_reduce_kernel, dim3(grid), dim3(256), 0, s, 1, ws, p.splits, n, C, out_f32,
+                               accumulate);
     if (e != cudaSuccess) return -500 - static_cast<int>(e);
   }
   return 0;

@@ -15,6 +15,7 @@ using namespace mg;
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint2* __restrict__ idx, int N, int H, int W,
                    int V, int P, int Q, int k, int stride, int pad) {
+  pdl_prologue();
   const long long total = static_cast<long long>(N) * P * Q * V;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -57,6 +58,7 @@ maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint2* __
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx, uint4* __restrict__ dx, int N, int H,
                    int W, int V, int P, int Q, int k, int stride, int pad) {
+  pdl_prologue();
   const long long total = static_cast<long long>(N) * H * W * V;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -110,7 +112,7 @@ extern "C" int mg_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, i
   const long long total = static_cast<long long>(N) * P * Q * (C / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
-  maxpool_fwd_kernel<<<static_cast<int>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(maxpool_fwd_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1,
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), reinterpret_cast<uint2*>(idx), N, H, W, C / 8, P, Q,
       k, stride, pad);
   return check();
@@ -124,7 +126,7 @@ extern "C" int mg_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, 
   const long long total = static_cast<long long>(N) * H * W * (C / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
-  maxpool_bwd_kernel<<<static_cast<int>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(maxpool_bwd_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1,
       reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint2*>(idx), reinterpret_cast<uint4*>(dx), N, H, W,
       C / 8, P, Q, k, stride, pad);
   return check();
