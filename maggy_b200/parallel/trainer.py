@@ -16,6 +16,33 @@ from ..utils import tracing
 from .arena import FlatParams, FusedAdamW
 
 
+_GRAPH_POOLS: dict = {}
+
+
+def _shared_graph_pool(device):
+    """One graph memory pool per device for the life of the process, kept alive by a one-node graph.
+
+    An HPO worker captures a fresh step graph for every trial. With a private pool per graph, destroying trial N's
+    graph ``cudaFree``s its several GB of activations and trial N+1's capture ``cudaMalloc``s them again — 0.2-1 s
+    per trial, as much as 100 training steps of ResNet-50 (profiles/resnet_r2/trial_startup.md). Sharing the pool
+    hands the blocks from one trial's graph straight to the next one's. ``MAGGY_B200_GRAPH_POOL=private`` restores
+    the per-graph pools."""
+    import os
+
+    if os.environ.get("MAGGY_B200_GRAPH_POOL", "shared") == "private":
+        return None
+    key = torch.device(device).index or 0
+    entry = _GRAPH_POOLS.get(key)
+    if entry is None:
+        pool = torch.cuda.graph_pool_handle()
+        keep = torch.cuda.CUDAGraph()
+        buf = torch.zeros(8, device=device)
+        with torch.cuda.graph(keep, pool=pool):
+            buf.add_(1.0)
+        entry = _GRAPH_POOLS[key] = (pool, keep, buf)
+    return entry[0]
+
+
 class TrainStep:
     """``step(idx_host, tgt_host) -> loss`` (device scalar). Inputs may be pinned host or device tensors."""
 
@@ -60,7 +87,7 @@ class TrainStep:
         torch.cuda.synchronize(self.device)
         before = F.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, pool=_shared_graph_pool(self.device)):
             self._eager()
         self.kernels_per_step = F.launch_count() - before
         self._captured = True
