@@ -44,6 +44,7 @@ class HyperparameterOptDriver(Driver):
     experiment_type = "optimization"
 
     _resumable: dict = {}   # class-level defaults: subclasses with their own constructor (ablation) never resume
+    _device_asha = False    # ... and never hand their next-trial decision to the device scheduler
     resumed_trials = 0
 
     def __init__(self, config, app_id, run_id):
@@ -142,6 +143,12 @@ class HyperparameterOptDriver(Driver):
         self.channel.configure_policy(host_engine, self.direction, self.es_min, self.es_interval)
         self.device_scheduler = None
         self.device_scheduler_stats = None
+        # ASHA rung bookkeeping + the promote / fresh-configuration decision on the device (K9); the driver samples
+        self._device_asha = False
+        self._dec_expected = {}
+        self.device_decisions = 0
+        self.device_decision_fallbacks = 0
+        self.device_decision_latencies = []
         self._start_device_scheduler()
 
     def _start_device_scheduler(self) -> None:
@@ -156,7 +163,11 @@ class HyperparameterOptDriver(Driver):
         over after the workers took theirs (GPU ``num_executors * gpus_per_worker``); ``=1`` forces it onto cuda:0
         (used by the tests and by single-GPU debugging), ``=0`` disables it."""
         mode = os.environ.get("MAGGY_B200_DEVICE_SCHED", "auto").lower()
-        if not self._native_policy or mode in ("0", "off", "false") or self.num_executors > 32:
+        from ...optimizer.asha import Asha
+
+        want_asha = isinstance(self.controller, Asha) and type(self.controller).get_suggestion is Asha.get_suggestion \
+            and os.environ.get("MAGGY_B200_DEVICE_ASHA", "1") != "0" and not self._resumable
+        if not (self._native_policy or want_asha) or mode in ("0", "off", "false") or self.num_executors > 32:
             return
         try:
             import torch
@@ -175,12 +186,22 @@ class HyperparameterOptDriver(Driver):
                 return
             from ..sched_kernel import DeviceScheduler
 
-            self.device_scheduler = DeviceScheduler(self.channel, direction=self.direction, es_min=self.es_min,
-                                                    es_interval=self.es_interval, device=f"cuda:{dev}").start()
+            asha = None
+            if want_asha and self.controller.max_rung < 8:
+                asha = {"rf": self.controller.reduction_factor, "max_rung": self.controller.max_rung,
+                        "cap": max(64, 2 * int(self.num_trials))}
+            # without a device-decidable early-stop policy K9 only schedules: an unreachable es_min disarms the rule
+            es_min = self.es_min if self._native_policy else 0x7fffffff
+            self.device_scheduler = DeviceScheduler(self.channel, direction=self.direction, es_min=es_min,
+                                                    es_interval=self.es_interval, device=f"cuda:{dev}",
+                                                    asha=asha).start()
+            self._device_asha = asha is not None
             self.log(f"device scheduler (K9) running on cuda:{dev}, "
-                     f"mailbox={'yes' if self.device_scheduler.mailbox else 'no'}")
+                     f"mailbox={'yes' if self.device_scheduler.mailbox else 'no'}, "
+                     f"asha_on_device={'yes' if self._device_asha else 'no'}")
         except Exception as e:  # noqa: BLE001 - the host policy engine covers every decision on its own
             self.device_scheduler = None
+            self._device_asha = False
             self.log(f"device scheduler not started: {type(e).__name__}: {e}")
 
     def stop(self) -> None:
@@ -211,8 +232,28 @@ class HyperparameterOptDriver(Driver):
     def controller_get_next(self, trial=None):
         return self.controller.get_suggestion(trial)
 
-    def _suggest(self, finished_trial=None):
+    def _device_suggest(self, worker, finished_trial):
+        """K9 filed ``finished_trial`` in its rung and decided what ``worker`` runs next; apply that decision. Returns
+        ``(handled, suggestion)``; not handled = no decision arrived in time and the host controller decides."""
+        expected = self._dec_expected.get(worker, 0)
+        dec = self.channel.device_decision(worker, expected) if expected > 0 else None
+        if dec is None:
+            self.device_decision_fallbacks += 1
+            return False, None
+        kind, rung, parent, t_ns = dec
+        self.device_decisions += 1
+        if getattr(finished_trial, "_final_t_ns", None):
+            self.device_decision_latencies.append((t_ns - finished_trial._final_t_ns) / 1e6)
+        with self._controller_lock:
+            return True, self.controller.apply_device_decision(kind, rung, parent, finished_trial)
+
+    def _suggest(self, finished_trial=None, worker=None):
         """Next Trial | "IDLE" | None. Uses the lookahead buffer when it holds something."""
+        if self._device_asha and finished_trial is not None and worker is not None \
+                and getattr(finished_trial, "_device_tagged", False):
+            handled, nxt = self._device_suggest(worker, finished_trial)
+            if handled:
+                return nxt
         if self._lookahead_enabled:
             t = self._lookahead_thread
             if t is not None and not t.is_alive():
@@ -260,7 +301,7 @@ class HyperparameterOptDriver(Driver):
             self._controller_exhausted = True
             self._maybe_finish()
             return
-        nxt = self._suggest(finished_trial)
+        nxt = self._suggest(finished_trial, worker)
         if nxt is None:
             self._controller_exhausted = True
             self._idle.pop(worker, None)
@@ -288,7 +329,11 @@ class HyperparameterOptDriver(Driver):
         trial.status = Trial.SCHEDULED
         trial.start = time.time()
         payload = {"params": trial.params, "trial_type": trial.trial_type}
-        while not self.channel.assign(worker, trial.trial_id, payload):
+        tag = 0
+        if self._device_asha:
+            tag = self.controller.rung_of(trial) + 1   # echoed in the FINAL record: K9 files the result in this rung
+            trial._device_tagged = True
+        while not self.channel.assign(worker, trial.trial_id, payload, tag):
             time.sleep(0.0005)  # the worker has not picked up its previous assignment yet
         trial.status = Trial.RUNNING
         self._assigned[worker] = trial.trial_id
@@ -418,6 +463,10 @@ class HyperparameterOptDriver(Driver):
             self._final_store.append(trial)
             self._trial_store.pop(trial.trial_id, None)
         self._assigned.pop(worker, None)
+        if getattr(trial, "_device_tagged", False):
+            # K9 takes exactly one next-trial decision per tagged FINAL of this worker
+            self._dec_expected[worker] = self._dec_expected.get(worker, 0) + 1
+            trial._final_t_ns = msg.get("t_ns")
         tracing.instant("final", worker=worker, trial=trial.trial_id, metric=trial.final_metric)
         # hand the worker its next trial first, do the bookkeeping while it is already training
         self._assign_next(worker, trial, t_final)
@@ -504,7 +553,13 @@ class HyperparameterOptDriver(Driver):
             exp["config"] = json.dumps(self.result.get("best_config"), default=util.json_default_numpy)
             exp["metric"] = self.result.get("best_val")
             if getattr(self, "device_scheduler_stats", None):
-                exp["device_scheduler"] = self.device_scheduler_stats   # K9 counters: polls / metrics / stops / mailbox
+                exp["device_scheduler"] = dict(self.device_scheduler_stats)  # K9 counters: polls / metrics / stops / mailbox
+                if getattr(self, "_device_asha", False) or getattr(self, "device_decisions", 0):
+                    lat = sorted(getattr(self, "device_decision_latencies", []))
+                    exp["device_scheduler"].update({
+                        "asha_decisions_applied": self.device_decisions,
+                        "asha_decision_fallbacks": self.device_decision_fallbacks,
+                        "final_to_decision_ms_median": lat[len(lat) // 2] if lat else None})
         else:
             exp["status"] = "RUNNING"
         return json.dumps(exp, default=util.json_default_numpy)

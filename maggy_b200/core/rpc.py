@@ -83,6 +83,11 @@ def _host():
     sig("mgr_check_stop", [P, u32, u64])
     sig("mgr_gstop_set", [P])
     sig("mgr_assign", [P, u32, u64, ctypes.c_char_p, u32])
+    sig("mgr_assign_tagged", [P, u32, u64, ctypes.c_char_p, u32, u32])
+    sig("mgr_decision", [P, u32, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u64), ctypes.POINTER(u64)], u32)
+    sig("mgr_asha_create", [u32, u32, u32, ctypes.c_int], P)
+    sig("mgr_asha_free", [P], None)
+    sig("mgr_asha_final", [P, u32, u64, ctypes.c_double, ctypes.POINTER(u64), ctypes.POINTER(u32)], u32)
     sig("mgr_stop_trial", [P, u32, u64], None)
     sig("mgr_gstop", [P], None)
     sig("mgr_read_blob", [P, u32, P, u32])
@@ -169,18 +174,32 @@ class DriverChannel:
         return out
 
     # -- send ------------------------------------------------------------------------------------
-    def assign(self, worker: int, trial_id: str, payload) -> bool:
-        """Place a trial in the worker's assign slot. False if the previous one was not picked up yet."""
+    def assign(self, worker: int, trial_id: str, payload, tag: int = 0) -> bool:
+        """Place a trial in the worker's assign slot. False if the previous one was not picked up yet. ``tag`` (ASHA:
+        rung + 1) is echoed in the trial's FINAL record for the device scheduler (mg_ring.h ``assign_tag``)."""
         blob = cloudpickle.dumps(payload)
         if len(blob) > self.payload_bytes:
             raise ValueError(f"trial payload of {len(blob)} bytes exceeds the {self.payload_bytes}-byte assign slot")
-        rc = self.lib.mgr_assign(self.h, worker, int(trial_id, 16), blob, len(blob))
+        rc = self.lib.mgr_assign_tagged(self.h, worker, int(trial_id, 16), blob, len(blob), int(tag))
         if rc == -2:
             return False
         if rc != 0:
             raise OSError(f"mgr_assign failed: {rc}")
         self.reservations.assign_trial(worker, trial_id)
         return True
+
+    def device_decision(self, worker: int, expected_seq: int, timeout_s: float = 0.002):
+        """The device scheduler's ``expected_seq``-th next-trial decision for ``worker`` (mg_asha.h) as
+        ``(kind, rung, parent_trial_id_hex, t_ns)``, or None if K9 has not published it within ``timeout_s``."""
+        kind, rung, parent, t_ns = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint64(), ctypes.c_uint64()
+        deadline = time.perf_counter() + timeout_s
+        while True:
+            seq = int(self.lib.mgr_decision(self.h, worker, ctypes.byref(kind), ctypes.byref(rung), ctypes.byref(parent),
+                                            ctypes.byref(t_ns)))
+            if seq == expected_seq:
+                return int(kind.value), int(rung.value), f"{parent.value:016x}", int(t_ns.value)
+            if seq > expected_seq or time.perf_counter() > deadline:
+                return None
 
     def stop_trial(self, worker: int, trial_id: str):
         self.lib.mgr_stop_trial(self.h, worker, int(trial_id, 16))

@@ -18,7 +18,12 @@ from . import rpc
 
 class DeviceScheduler:
     def __init__(self, channel: "rpc.DriverChannel", direction: str = "max", es_min: int = 10, es_interval: int = 1,
-                 max_steps: int = 1024, cap_final: int = 1024, device="cuda:0", use_mailbox: bool = True):
+                 max_steps: int = 1024, cap_final: int = 1024, device="cuda:0", use_mailbox: bool = True,
+                 asha: dict = None):
+        """``asha={"rf": 2, "max_rung": 2, "cap": 256}``: K9 also keeps the ASHA rung tables and takes the next-trial
+        decision (promote which configuration / start a fresh one) when it sees a worker's FINAL record
+        (csrc/include/mg_asha.h; reference: maggy/optimizer/asha.py:95-147 on the driver)."""
+        self.asha = asha
         self.ch = channel
         self.device = torch.device(device)
         self.direction = 1 if direction == "max" else -1
@@ -30,7 +35,9 @@ class DeviceScheduler:
         self.cu.mg_ring_map.argtypes, self.cu.mg_ring_map.restype = [P, u64], u64
         self.cu.mg_sched_scratch_bytes.argtypes, self.cu.mg_sched_scratch_bytes.restype = [u32, u32, u32], u64
         self.cu.mg_sched_start.argtypes = [u64, u64, u64, u64, u64, u32, u32, i32, u32, u32, u32, u32, P, u64, u64, u32,
-                                           ctypes.c_longlong, P]
+                                           ctypes.c_longlong, P, P]
+        self.cu.mg_asha_table_bytes.argtypes, self.cu.mg_asha_table_bytes.restype = [u32], u64
+        self.asha_table = None
         self.cu.mg_sched_start.restype = i32
         self.cu.mg_mailbox_create.argtypes, self.cu.mg_mailbox_create.restype = [u32, u32, ctypes.c_char_p], u64
         self.cu.mg_mailbox_free.argtypes, self.cu.mg_mailbox_free.restype = [u64], i32
@@ -73,11 +80,23 @@ class DeviceScheduler:
                     host.mgr_set_mailbox(h, handle.raw, self.mailbox_slots,
                                          W * (64 + 64 * self.mailbox_slots))
             self.gt_offset = int(self.cu.mg_gt_offset_ns())
+            asha_ptr = None
+            if self.asha:
+                import struct
+
+                cap = int(self.asha.get("cap", 256))
+                nbytes = int(self.cu.mg_asha_table_bytes(cap))
+                host_tab = torch.zeros(nbytes, dtype=torch.uint8)
+                hdr = struct.pack("<IIIi", int(self.asha["rf"]), int(self.asha["max_rung"]), cap, self.direction)
+                host_tab[:len(hdr)] = torch.frombuffer(bytearray(hdr), dtype=torch.uint8)
+                self.asha_table = host_tab.to(self.device)
+                torch.cuda.synchronize(self.device)
+                asha_ptr = self.asha_table.data_ptr()
             rc = self.cu.mg_sched_start(base, off_ctl, off_host0, off_dev0, ring_stride, W,
                                         int(host.mgr_ring_slots(h)), self.direction, self.es_min, self.es_interval,
                                         self.max_steps, self.cap_final, self.scratch.data_ptr(), quit_dev,
                                         self.mailbox, self.mailbox_slots if self.mailbox else 0, self.gt_offset,
-                                        self.stream.cuda_stream)
+                                        asha_ptr, self.stream.cuda_stream)
             if rc != 0:
                 raise RuntimeError(f"mg_sched_start failed: {rc}")
         self.running = True
@@ -98,9 +117,9 @@ class DeviceScheduler:
         W = self.ch.num_workers
         off = 4 * self.cap_final * self.max_steps + 4 * self.cap_final + 8 + 4 * W * self.max_steps
         off = (off + 7) // 8 * 8 + 8 * W * 3
-        raw = self.scratch[off:off + 40].cpu().view(torch.int64).tolist()
+        raw = self.scratch[off:off + 48].cpu().view(torch.int64).tolist()
         return {"polls": raw[0], "metrics": raw[1], "stops": raw[2], "finals": raw[3], "mailbox_records": raw[4],
-                "mailbox": bool(self.mailbox)}
+                "asha_decisions": raw[5], "mailbox": bool(self.mailbox)}
 
     def stop(self) -> dict:
         if self.running:

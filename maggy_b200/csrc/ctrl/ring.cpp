@@ -9,6 +9,7 @@
 // a STOP word is written microseconds after the offending METRIC record lands, independent of the
 // Python GIL — and hands the records to Python through an in-process queue.
 #include "../include/mg_ring.h"
+#include "../include/mg_asha.h"
 
 #include <algorithm>
 #include <atomic>
@@ -239,7 +240,9 @@ int post_record(Handle* h, uint32_t w, uint16_t type, uint64_t trial_id, int64_t
   s->step = step;
   s->value = value;
   s->t_ns = now_ns();
-  s->reserved[0] = s->reserved[1] = 0;
+  // FINAL echoes the tag the driver attached to the assignment (ASHA: rung + 1) so the device scheduler can file it
+  s->reserved[0] = type == MG_REC_FINAL ? h->ctl(w)->assign_tag : 0;
+  s->reserved[1] = 0;
   store_rel(&s->seq, head + 1);
   store_rel(&rg->head, head + 1);
   __atomic_fetch_add(&hd->doorbell, 1u, __ATOMIC_RELEASE);
@@ -494,7 +497,13 @@ int mgr_gstop_set(void* hv) {
 // ---------------------------------------------------------------------------------------------------
 // driver side
 // ---------------------------------------------------------------------------------------------------
+int mgr_assign_tagged(void* hv, uint32_t w, uint64_t trial_id, const void* data, uint32_t len, uint32_t tag);
 int mgr_assign(void* hv, uint32_t w, uint64_t trial_id, const void* data, uint32_t len) {
+  return mgr_assign_tagged(hv, w, trial_id, data, len, 0);
+}
+
+// tag: opaque, echoed in the trial's FINAL record (ASHA: rung + 1; 0 = untagged, no device decision is taken)
+int mgr_assign_tagged(void* hv, uint32_t w, uint64_t trial_id, const void* data, uint32_t len, uint32_t tag) {
   Handle* h = static_cast<Handle*>(hv);
   MgHeader* hd = h->hdr();
   if (w >= hd->num_workers || len > hd->payload_bytes) return -1;
@@ -503,6 +512,7 @@ int mgr_assign(void* hv, uint32_t w, uint64_t trial_id, const void* data, uint32
   if (len) std::memcpy(h->assign_buf(w), data, len);
   c->assign_len = len;
   c->assign_trial_id = trial_id;
+  c->assign_tag = tag;
   store_rel(&c->stop_trial_id, static_cast<uint64_t>(0));
   store_rel(&c->assign_seq, c->assign_seq + 1);
   futex_wake_all(&c->assign_seq);
@@ -546,6 +556,35 @@ uint64_t mgr_dev_dropped(void* hv, uint32_t w) {
   return load_acq(&static_cast<Handle*>(hv)->ring(true, w)->dropped);
 }
 uint64_t mgr_stop_time_ns(void* hv, uint32_t w) { return static_cast<Handle*>(hv)->ctl(w)->stop_t_ns; }
+
+// the device scheduler's n-th next-trial decision for worker w: returns dec_seq (acquire) and fills the fields
+uint32_t mgr_decision(void* hv, uint32_t w, uint32_t* kind, uint32_t* rung, uint64_t* parent, uint64_t* t_ns) {
+  MgWorkerCtl* c = static_cast<Handle*>(hv)->ctl(w);
+  const uint32_t seq = load_acq(&c->dec_seq);
+  *kind = c->dec_kind;
+  *rung = c->dec_rung;
+  *parent = c->dec_parent;
+  *t_ns = c->dec_t_ns;
+  return seq;
+}
+
+// ---- the rung tables of mg_asha.h on the host: the oracle the CPU tests compare maggy_b200.optimizer.Asha against
+void* mgr_asha_create(uint32_t rf, uint32_t max_rung, uint32_t cap, int32_t direction) {
+  void* mem = std::calloc(1, mg_asha_bytes(cap));
+  if (!mem) return nullptr;
+  MgAsha* a = static_cast<MgAsha*>(mem);
+  a->rf = rf;
+  a->max_rung = max_rung;
+  a->cap = cap;
+  a->direction = direction;
+  return mem;
+}
+void mgr_asha_free(void* a) { std::free(a); }
+uint32_t mgr_asha_final(void* av, uint32_t rung, uint64_t trial_id, double metric, uint64_t* parent, uint32_t* rung_out) {
+  MgAsha* a = static_cast<MgAsha*>(av);
+  mg_asha_record(a, rung, trial_id, metric);
+  return mg_asha_decide(a, parent, rung_out);
+}
 
 void mgr_policy_config(void* hv, uint32_t enabled, int32_t direction, uint32_t es_min,
                        uint32_t es_interval) {

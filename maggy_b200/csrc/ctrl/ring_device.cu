@@ -25,6 +25,7 @@
 // worker's heartbeat word (the host heartbeat thread owns it).
 #include "../include/mg_ptx.cuh"
 #include "../include/mg_ring.h"
+#include "../include/mg_asha.h"
 
 #include <string.h>
 #include <time.h>
@@ -130,10 +131,13 @@ struct SchedArgs {
   float* run_tab;            // [num_workers][max_steps] prefix averages of the running trial
   unsigned long long* cursors;  // [num_workers][3]: host ring, host-mapped device ring, mailbox ring
   volatile unsigned int* quit;  // host-mapped: != 0 terminates the kernel
-  unsigned long long* stats;    // [0] polls, [1] metrics seen, [2] stops issued, [3] finals seen, [4] mailbox records
+  unsigned long long* stats;    // [0] polls, [1] metrics seen, [2] stops issued, [3] finals seen, [4] mailbox records,
+                                // [5] next-trial (ASHA) decisions
   uint8_t* mailbox;             // device mailbox (local HBM) or nullptr
   unsigned int mbox_slots;
   long long gt_offset_ns;
+  MgAsha* asha;                 // rung tables (device memory) or nullptr: next-trial decisions are taken here
+  unsigned int* asha_lock;      // [1] the worker threads of this CTA file finals one at a time
 };
 
 struct RunState {
@@ -261,6 +265,32 @@ sched_kernel(const SchedArgs a) {
             }
             rs.trial_id = 0; rs.n = 0; rs.sum = 0; rs.last_step = LLONG_MIN; rs.stopped = false;
             atomicAdd(&a.stats[3], 1ull);
+            const unsigned long long tag = s->reserved[0];
+            if (a.asha != nullptr && tag > 0) {
+              // ASHA on the device (reference: maggy/optimizer/asha.py:95-147 runs on the driver after the FINAL
+              // message): file the result in its rung, scan for a promotable configuration, publish the decision
+              // for this worker. The driver only materialises it (samples / copies the hyperparameters).
+              unsigned long long parent = 0;
+              unsigned int rung = 0, kind = MG_DEC_NONE;
+              bool done = false;
+              while (!done) {
+                if (atomicCAS(a.asha_lock, 0u, 1u) == 0u) {
+                  __threadfence();
+                  mg_asha_record(a.asha, static_cast<unsigned int>(tag - 1), tid, value);
+                  kind = mg_asha_decide(a.asha, reinterpret_cast<uint64_t*>(&parent), &rung);
+                  __threadfence();
+                  atomicExch(a.asha_lock, 0u);
+                  done = true;
+                }
+              }
+              ctl->dec_kind = kind;
+              ctl->dec_rung = rung;
+              ctl->dec_parent = parent;
+              ctl->dec_t_ns = globaltimer_ns() + static_cast<unsigned long long>(a.gt_offset_ns);
+              __threadfence_system();
+              red_release_sys_add_u32(&ctl->dec_seq, 1u);
+              atomicAdd(&a.stats[5], 1ull);
+            }
           }
         }
         a.cursors[w * 3 + which] = cur;
@@ -380,13 +410,16 @@ unsigned long long mg_sched_scratch_bytes(unsigned int num_workers, unsigned int
   return b;
 }
 
+// bytes of the device buffer mg_sched_start's asha_table needs: header + rung tables + the lock word
+unsigned long long mg_asha_table_bytes(unsigned int cap) { return mg_asha_bytes(cap) + 8; }
+
 int mg_sched_start(unsigned long long dev_base, unsigned long long off_ctl,
                    unsigned long long off_host_ring, unsigned long long off_dev_ring,
                    unsigned long long ring_stride, unsigned int num_workers, unsigned int slots,
                    int direction, unsigned int es_min, unsigned int es_interval,
                    unsigned int max_steps, unsigned int cap_final, void* scratch,
                    unsigned long long quit_dev_ptr, unsigned long long mailbox, unsigned int mbox_slots,
-                   long long gt_offset_ns, void* stream) {
+                   long long gt_offset_ns, void* asha_table, void* stream) {
   if (num_workers > 32) return -1;
   SchedArgs a;
   a.base = reinterpret_cast<uint8_t*>(dev_base);
@@ -406,6 +439,16 @@ int mg_sched_start(unsigned long long dev_base, unsigned long long off_ctl,
   a.mailbox = reinterpret_cast<uint8_t*>(mailbox);
   a.mbox_slots = mbox_slots;
   a.gt_offset_ns = gt_offset_ns;
+  // asha_table: device buffer of mg_asha_table_bytes(cap) bytes whose MgAsha header (rf, max_rung, cap, direction) the
+  // caller filled in and whose remainder is zero; null = next-trial decisions stay on the driver
+  a.asha = reinterpret_cast<MgAsha*>(asha_table);
+  a.asha_lock = nullptr;
+  if (asha_table != nullptr) {
+    unsigned int cap = 0;
+    if (cudaMemcpy(&cap, reinterpret_cast<uint8_t*>(asha_table) + 8, 4, cudaMemcpyDeviceToHost) != cudaSuccess || cap == 0)
+      return -2;
+    a.asha_lock = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(asha_table) + mg_asha_bytes(cap));
+  }
   sched_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);

@@ -14,11 +14,12 @@
 //   GET/TRIAL -> driver writes the assign slot (+payload) and bumps assign_seq; worker futex-waits
 //   STOP  -> driver/policy writes ctl.stop_trial_id; GSTOP -> header.gstop
 //   BLACK -> heartbeat timeout / re-REG with a trial still assigned (handled by the driver)
+//   next-trial decision (ASHA rung scan) -> K9 writes ctl.dec_* when it sees a tagged FINAL (mg_asha.h)
 #pragma once
 #include <stdint.h>
 
 #define MG_RING_MAGIC 0x4d47523162323030ull /* "MGR1b200" */
-#define MG_RING_VERSION 3u
+#define MG_RING_VERSION 4u
 
 enum MgRecType : uint16_t {
   MG_REC_NONE = 0,
@@ -61,7 +62,7 @@ struct alignas(64) MgWorkerCtl {
   uint64_t assign_trial_id;
   uint64_t stop_trial_id;            // != 0: the trial with this id must stop at its next broadcast
   uint32_t stop_seq;                 // bumped with every stop request
-  uint32_t pad0;
+  uint32_t assign_tag;               // opaque tag of the assigned trial (ASHA: rung + 1), echoed in its FINAL record
   uint64_t stop_t_ns;                // when the stop decision was taken (latency accounting)
   // ---- written by the worker
   alignas(64) uint64_t heartbeat_ns; // last sign of life
@@ -73,6 +74,13 @@ struct alignas(64) MgWorkerCtl {
   uint32_t pid;
   // ---- written by the driver
   alignas(64) uint32_t blob_ack;     // driver consumed blob #blob_ack
+  // ---- written by the persistent scheduler kernel (K9): what the worker should run after its n-th tagged FINAL
+  alignas(64) uint32_t dec_seq;      // decisions taken for this worker so far (release-stored last)
+  uint32_t dec_kind;                 // MgDecision (mg_asha.h)
+  uint32_t dec_rung;                 // PROMOTE: rung the parent finished in
+  uint32_t dec_pad;
+  uint64_t dec_parent;               // PROMOTE: trial id of the configuration to promote
+  uint64_t dec_t_ns;                 // when K9 took the decision
 };
 
 enum MgWorkerState : uint32_t {

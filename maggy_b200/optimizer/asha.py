@@ -70,6 +70,41 @@ class Asha(AbstractOptimizer):
             return child
         return None
 
+    # ---- device-side decisions (K9, csrc/include/mg_asha.h) ------------------------------------------------------
+    NEW, PROMOTE = 1, 2
+
+    def rung_of(self, trial) -> int:
+        budget = trial.params.get("budget", self.resource_min)
+        return int(round(math.log(max(budget, 1) / self.resource_min, self.reduction_factor)))
+
+    def _child_of(self, parent, rung):
+        params = dict(parent.params)
+        params["budget"] = self.budget_of(rung + 1)
+        child = Trial(params, info_dict={"run_budget": params["budget"], "sample_type": "promoted",
+                                         "parent": parent.trial_id})
+        self.rungs.setdefault(rung + 1, []).append(child)
+        self.promoted.setdefault(rung, []).append(parent.trial_id)
+        return child
+
+    def apply_device_decision(self, kind, rung, parent_id, trial=None):
+        """Materialise a next-trial decision the persistent scheduler kernel took from its own rung tables: the driver
+        only copies / samples the hyperparameters. Falls back to :meth:`get_suggestion` when the decision cannot be
+        honoured (unknown parent, or the host already promoted it after a missed decision)."""
+        if self.max_rung in self.rungs:
+            return None
+        if kind == self.PROMOTE:
+            parent = next((t for t in self.rungs.get(rung, []) if t.trial_id == parent_id), None)
+            if parent is None or parent.trial_id in self.promoted.setdefault(rung, []):
+                return self.get_suggestion(trial)
+            child = self._child_of(parent, rung)
+            self._log(f"[device] promote {parent.trial_id} from rung {rung} to rung {rung + 1} as {child.trial_id}")
+            return child
+        params = self.searchspace.get_random_parameter_values(1)[0]
+        params["budget"] = self.resource_min
+        fresh = Trial(params, info_dict={"run_budget": self.resource_min, "sample_type": "random"})
+        self.rungs[0].append(fresh)
+        return fresh
+
     def get_suggestion(self, trial=None):
         if trial is not None:
             if self.max_rung in self.rungs:

@@ -98,3 +98,56 @@ def test_device_scheduler_stops_trials_during_a_real_lagom_run(tmp_path, monkeyp
     assert short and lens[0] < 80, (lens, k9)     # (a STOP that lands on the very last report still counts as one)
     # the records K9 judged came out of the device mailbox (GPU memory reached through CUDA IPC), not host memory
     assert k9["mailbox"] and k9["mailbox_records"] > 50, k9
+
+
+def train_budgeted_quality_on_device(hparams, reporter):
+    """Quality = q; ``budget`` units of 6 reports each, published from the GPU."""
+    import torch
+
+    q = torch.tensor(float(hparams["q"]), device="cuda")
+    steps = 6 * int(hparams.get("budget", 1))
+    for step in range(steps):
+        reporter.broadcast(q + 1e-3 * step, step)
+    return float(hparams["q"]) + 1e-3 * (steps - 1)
+
+
+def test_asha_rung_decisions_are_taken_by_the_device_scheduler(tmp_path, monkeypatch):
+    """ASHA through lagom with K9 running: every FINAL of a tagged trial is filed in the rung tables ON THE GPU and the
+    promote / fresh-configuration decision the driver applies comes back from the kernel (no early-stop policy is
+    configured, K9 runs for the scheduling decision alone)."""
+    from maggy_b200 import Searchspace, experiment
+    from maggy_b200.config import HyperparameterOptConfig
+    from maggy_b200.core.environment.singleton import EnvSing
+    from maggy_b200.optimizer import Asha
+
+    monkeypatch.setenv("MAGGY_LOG_DIR", str(tmp_path / "experiment_log"))
+    monkeypatch.setenv("MAGGY_NUM_EXECUTORS", "1")
+    monkeypatch.setenv("MAGGY_B200_DEVICE_SCHED", "1")
+    EnvSing.reset()
+    sp = Searchspace(q=("DOUBLE", [0.0, 1.0]))
+    cfg = HyperparameterOptConfig(num_trials=16, optimizer=Asha(reduction_factor=2, resource_min=1, resource_max=4),
+                                  searchspace=sp, direction="max", es_policy="none", name="gpu_k9_asha", seed=5)
+    res = experiment.lagom(train_budgeted_quality_on_device, cfg)
+    EnvSing.reset()
+    root = str(tmp_path / "experiment_log")
+    app = os.path.join(root, sorted(os.listdir(root))[-1])
+    run = os.path.join(app, sorted(os.listdir(app), key=int)[-1])
+    meta = json.load(open(os.path.join(run, "maggy.json")))
+    log = open(os.path.join(run, "maggy.log")).read()
+    k9 = meta.get("device_scheduler")
+    assert k9 is not None and "asha_on_device=yes" in log, log[-3000:]
+    trials = [json.load(open(os.path.join(run, t, "trial.json"))) for t in os.listdir(run)
+              if os.path.exists(os.path.join(run, t, "trial.json"))]
+    budgets = sorted(t["params"]["budget"] for t in trials)
+    assert budgets[-1] == 4 and budgets.count(2) >= 2, budgets          # promotions up to the closing rung happened
+    # one device decision per finished trial (the last FINAL closes the experiment before its decision is read)
+    assert k9["asha_decisions"] >= len(trials) - 1, (k9, len(trials))
+    assert k9["asha_decisions_applied"] >= len(trials) - 2 and k9["asha_decision_fallbacks"] <= 1, k9
+    assert k9["stops"] == 0
+    # the promoted configurations are the ones the rung tables rank on top: parent of every budget-2 trial is in the
+    # better half of the budget-1 trials finished so far (checked loosely: better than the rung's worst)
+    worst_b1 = min(t["final_metric"] for t in trials if t["params"]["budget"] == 1)
+    for t in trials:
+        if t["params"]["budget"] == 2:
+            assert t["params"]["q"] > worst_b1 - 1e-2
+    assert res["num_trials"] == len(trials)

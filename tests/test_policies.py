@@ -347,3 +347,71 @@ def test_loco_feature_store_dataset_generator_drops_the_ablated_feature(tmp_path
     with pytest.raises(KeyError):
         loco.get_dataset_generator(ablated_feature="nope")(1, 4)
     EnvSing.reset()
+
+
+def test_device_asha_tables_agree_with_the_python_optimizer():
+    """csrc/include/mg_asha.h (the rung tables K9 keeps on the GPU; exercised here through the host library) takes the
+    same promote / fresh-configuration decisions as maggy_b200.optimizer.Asha on a random stream of results."""
+    import ctypes
+    import random
+
+    from maggy_b200 import Searchspace
+    from maggy_b200.core import rpc
+    from maggy_b200.optimizer import Asha
+    from maggy_b200.trial import Trial
+
+    lib = rpc._host()
+    for direction, rf, rmax in (("max", 2, 4), ("min", 3, 27), ("max", 2, 16)):
+        opt = Asha(reduction_factor=rf, resource_min=1, resource_max=rmax)
+        opt.searchspace = Searchspace(x=("DOUBLE", [0.0, 1.0]))
+        opt.searchspace.seed(1)
+        opt.num_trials, opt.direction = 4096, direction
+        opt.trial_store, opt.final_store = {}, []
+        opt.initialize()
+        opt.max_rung = 6   # far-away closing rung: compare a long decision stream
+        tab = lib.mgr_asha_create(rf, opt.max_rung, 512, 1 if direction == "max" else -1)
+        rng = random.Random(7)
+        running = [opt.get_suggestion() for _ in range(5)]
+        promotions = 0
+        for step in range(300):
+            t = running.pop(rng.randrange(len(running)))
+            t.status, t.final_metric = Trial.FINALIZED, rng.random()
+            parent, rung = ctypes.c_uint64(), ctypes.c_uint32()
+            kind = lib.mgr_asha_final(tab, opt.rung_of(t), int(t.trial_id, 16), t.final_metric, ctypes.byref(parent),
+                                      ctypes.byref(rung))
+            nxt = opt.get_suggestion(t)
+            if nxt is None:   # a configuration reached the closing rung
+                break
+            if nxt.info_dict["sample_type"] == "promoted":
+                promotions += 1
+                assert kind == Asha.PROMOTE, (direction, step)
+                assert f"{parent.value:016x}" == nxt.info_dict["parent"] and opt.rung_of(nxt) == rung.value + 1
+            else:
+                assert kind == Asha.NEW, (direction, step)
+            running.append(nxt)
+        assert promotions > 20 and step > 100
+        lib.mgr_asha_free(tab)
+
+
+def test_asha_applies_device_decisions_and_falls_back():
+    from maggy_b200 import Searchspace
+    from maggy_b200.optimizer import Asha
+    from maggy_b200.trial import Trial
+
+    opt = Asha(reduction_factor=2, resource_min=1, resource_max=4)
+    opt.searchspace = Searchspace(x=("DOUBLE", [0.0, 1.0]))
+    opt.num_trials, opt.direction = 64, "max"
+    opt.trial_store, opt.final_store = {}, []
+    opt.initialize()
+    a, b = opt.get_suggestion(), opt.get_suggestion()
+    for t, m in ((a, 0.3), (b, 0.9)):
+        t.status, t.final_metric = Trial.FINALIZED, m
+    child = opt.apply_device_decision(Asha.PROMOTE, 0, b.trial_id, b)
+    assert child.params["budget"] == 2 and child.info_dict["parent"] == b.trial_id and b.trial_id in opt.promoted[0]
+    assert opt.rung_of(child) == 1 and child in opt.rungs[1]
+    again = opt.apply_device_decision(Asha.PROMOTE, 0, b.trial_id, b)          # already promoted: host decides instead
+    assert again.info_dict["sample_type"] == "random"
+    unknown = opt.apply_device_decision(Asha.PROMOTE, 0, "00000000deadbeef", b)   # parent the host never placed
+    assert unknown.info_dict["sample_type"] == "random"
+    fresh = opt.apply_device_decision(Asha.NEW, 0, "0" * 16, a)
+    assert fresh.params["budget"] == 1 and fresh in opt.rungs[0]
