@@ -45,6 +45,7 @@ class HyperparameterOptDriver(Driver):
 
     _resumable: dict = {}   # class-level defaults: subclasses with their own constructor (ablation) never resume
     _device_asha = False    # ... and never hand their next-trial decision to the device scheduler
+    _staged: dict = {}
     resumed_trials = 0
 
     def __init__(self, config, app_id, run_id):
@@ -146,6 +147,8 @@ class HyperparameterOptDriver(Driver):
         # ASHA rung bookkeeping + the promote / fresh-configuration decision on the device (K9); the driver samples
         self._device_asha = False
         self._dec_expected = {}
+        self._staged = {}              # worker -> prefetched Trial parked in its staged slot
+        self.device_handoffs = 0
         self.device_decisions = 0
         self.device_decision_fallbacks = 0
         self.device_decision_latencies = []
@@ -237,6 +240,14 @@ class HyperparameterOptDriver(Driver):
         ``(handled, suggestion)``; not handled = no decision arrived in time and the host controller decides."""
         expected = self._dec_expected.get(worker, 0)
         dec = self.channel.device_decision(worker, expected) if expected > 0 else None
+        if dec is None and expected > 0 and worker in self._staged:
+            # A trial is parked for this worker, so K9 may still publish it: the driver must not write the assign words
+            # at the same time. K9 answers within microseconds unless its context is time-sliced against a trainer on
+            # the same GPU (forced single-GPU mode); give it 250 ms, then retire the device path for good.
+            dec = self.channel.device_decision(worker, expected, timeout_s=0.25)
+            if dec is None:
+                self.log("device scheduler did not answer within 250 ms: next-trial decisions return to the driver")
+                self._device_asha = False
         if dec is None:
             self.device_decision_fallbacks += 1
             return False, None
@@ -244,8 +255,31 @@ class HyperparameterOptDriver(Driver):
         self.device_decisions += 1
         if getattr(finished_trial, "_final_t_ns", None):
             self.device_decision_latencies.append((t_ns - finished_trial._final_t_ns) / 1e6)
+        if kind == 3:   # MG_DEC_NEW_PUBLISHED: K9 already handed the worker its prefetched trial
+            state, tid = self.channel.staged_state(worker)
+            parked = self._staged.pop(worker, None)
+            if state == "published" and parked is not None and parked.trial_id == tid:
+                parked._handoff_t_ns = t_ns
+                return True, parked
+            kind = 1    # (cannot happen unless the slot was re-staged in between): sample a fresh one the normal way
         with self._controller_lock:
             return True, self.controller.apply_device_decision(kind, rung, parent, finished_trial)
+
+    def _stage_prefetch(self, worker: int) -> None:
+        """Park a fresh rung-0 configuration in ``worker``'s staged slot: K9 publishes it (five words and a release
+        store from the GPU) the moment its rung scan says "nothing to promote" for that worker's next FINAL."""
+        if not self._device_asha or worker in self._staged or self.experiment_done or self._controller_exhausted:
+            return
+        if self._scheduled + len(self._staged) >= self.num_trials:
+            return
+        with self._controller_lock:
+            if self.controller.max_rung in self.controller.rungs:
+                return
+            trial = self.controller.fresh_trial()
+        payload = {"params": trial.params, "trial_type": trial.trial_type}
+        if self.channel.stage(worker, trial.trial_id, payload, self.controller.rung_of(trial) + 1):
+            trial._device_tagged = True
+            self._staged[worker] = trial
 
     def _suggest(self, finished_trial=None, worker=None):
         """Next Trial | "IDLE" | None. Uses the lookahead buffer when it holds something."""
@@ -316,10 +350,29 @@ class HyperparameterOptDriver(Driver):
             done = self._replay_finished(nxt)
             self._assign_next(worker, done, t_final)
             return
-        self._schedule(worker, nxt)
-        if t_final is not None:
-            self.inter_trial_gaps.append(time.time() - t_final)
+        handoff_t = getattr(nxt, "_handoff_t_ns", None)
+        if handoff_t is not None:
+            # the device scheduler published this (prefetched) trial already: bookkeeping only
+            self._adopt_published(worker, nxt)
+            if getattr(finished_trial, "_final_t_ns", None):
+                self.inter_trial_gaps.append(max(0.0, (handoff_t - finished_trial._final_t_ns) / 1e9))
+        else:
+            self._schedule(worker, nxt)
+            if t_final is not None:
+                self.inter_trial_gaps.append(time.time() - t_final)
+        self._stage_prefetch(worker)
         self._kick_lookahead(finished_trial)
+
+    def _adopt_published(self, worker: int, trial: Trial):
+        with self._store_lock:
+            self._trial_store[trial.trial_id] = trial
+        trial.start = time.time()
+        trial.status = Trial.RUNNING
+        self._assigned[worker] = trial.trial_id
+        self._scheduled += 1
+        self.device_handoffs += 1
+        self.channel.reservations.assign_trial(worker, trial.trial_id)
+        tracing.instant("assign", worker=worker, trial=trial.trial_id, handoff="device")
 
     def _schedule(self, worker: int, trial: Trial):
         with self._store_lock:
@@ -335,6 +388,12 @@ class HyperparameterOptDriver(Driver):
             trial._device_tagged = True
         while not self.channel.assign(worker, trial.trial_id, payload, tag):
             time.sleep(0.0005)  # the worker has not picked up its previous assignment yet
+        parked = self._staged.pop(worker, None)
+        if parked is not None:
+            # a direct assignment invalidates the parked entry (its sequence number is taken): park it again
+            if self.channel.stage(worker, parked.trial_id, {"params": parked.params, "trial_type": parked.trial_type},
+                                  self.controller.rung_of(parked) + 1):
+                self._staged[worker] = parked
         trial.status = Trial.RUNNING
         self._assigned[worker] = trial.trial_id
         self._scheduled += 1
@@ -558,6 +617,7 @@ class HyperparameterOptDriver(Driver):
                     lat = sorted(getattr(self, "device_decision_latencies", []))
                     exp["device_scheduler"].update({
                         "asha_decisions_applied": self.device_decisions,
+                        "prefetched_handoffs_adopted": self.device_handoffs,
                         "asha_decision_fallbacks": self.device_decision_fallbacks,
                         "final_to_decision_ms_median": lat[len(lat) // 2] if lat else None})
         else:

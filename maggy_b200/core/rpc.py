@@ -84,6 +84,9 @@ def _host():
     sig("mgr_gstop_set", [P])
     sig("mgr_assign", [P, u32, u64, ctypes.c_char_p, u32])
     sig("mgr_assign_tagged", [P, u32, u64, ctypes.c_char_p, u32, u32])
+    sig("mgr_stage", [P, u32, u64, ctypes.c_char_p, u32, u32])
+    sig("mgr_staged_state", [P, u32, ctypes.POINTER(u64)])
+    sig("mgr_publish_staged", [P, u32])
     sig("mgr_decision", [P, u32, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u64), ctypes.POINTER(u64)], u32)
     sig("mgr_asha_create", [u32, u32, u32, ctypes.c_int], P)
     sig("mgr_asha_free", [P], None)
@@ -187,6 +190,29 @@ class DriverChannel:
             raise OSError(f"mgr_assign failed: {rc}")
         self.reservations.assign_trial(worker, trial_id)
         return True
+
+    def stage(self, worker: int, trial_id: str, payload, tag: int = 0) -> bool:
+        """Park ``worker``'s NEXT trial in its staged slot (prefetch): the device scheduler — or :meth:`publish_staged`
+        — hands it over the moment the worker's FINAL shows up. False if a trial is already parked there."""
+        blob = cloudpickle.dumps(payload)
+        if len(blob) > self.payload_bytes:
+            raise ValueError(f"trial payload of {len(blob)} bytes exceeds the {self.payload_bytes}-byte staged slot")
+        rc = self.lib.mgr_stage(self.h, worker, int(trial_id, 16), blob, len(blob), int(tag))
+        if rc not in (0, -2):
+            raise OSError(f"mgr_stage failed: {rc}")
+        return rc == 0
+
+    def staged_state(self, worker: int):
+        """``("parked" | "published" | None, trial_id_hex)`` for the worker's staged slot."""
+        tid = ctypes.c_uint64()
+        rc = int(self.lib.mgr_staged_state(self.h, worker, ctypes.byref(tid)))
+        return ({1: "parked", 2: "published"}.get(rc), f"{tid.value:016x}")
+
+    def publish_staged(self, worker: int) -> bool:
+        ok = int(self.lib.mgr_publish_staged(self.h, worker)) == 0
+        if ok:
+            self.reservations.assign_trial(worker, self.staged_state(worker)[1])
+        return ok
 
     def device_decision(self, worker: int, expected_seq: int, timeout_s: float = 0.002):
         """The device scheduler's ``expected_seq``-th next-trial decision for ``worker`` (mg_asha.h) as

@@ -117,9 +117,9 @@ class DeviceScheduler:
         W = self.ch.num_workers
         off = 4 * self.cap_final * self.max_steps + 4 * self.cap_final + 8 + 4 * W * self.max_steps
         off = (off + 7) // 8 * 8 + 8 * W * 3
-        raw = self.scratch[off:off + 48].cpu().view(torch.int64).tolist()
+        raw = self.scratch[off:off + 56].cpu().view(torch.int64).tolist()
         return {"polls": raw[0], "metrics": raw[1], "stops": raw[2], "finals": raw[3], "mailbox_records": raw[4],
-                "asha_decisions": raw[5], "mailbox": bool(self.mailbox)}
+                "asha_decisions": raw[5], "handoffs": raw[6], "mailbox": bool(self.mailbox)}
 
     def stop(self) -> dict:
         if self.running:

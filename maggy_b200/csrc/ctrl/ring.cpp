@@ -105,6 +105,9 @@ struct Handle {
   uint8_t* assign_buf(uint32_t w) const {
     return base + hdr()->off_assign + static_cast<uint64_t>(w) * hdr()->payload_bytes;
   }
+  uint8_t* staged_buf(uint32_t w) const {
+    return base + hdr()->off_staged + static_cast<uint64_t>(w) * hdr()->payload_bytes;
+  }
   uint8_t* blob_buf(uint32_t w) const {
     return base + hdr()->off_blob + static_cast<uint64_t>(w) * hdr()->payload_bytes;
   }
@@ -277,6 +280,8 @@ void* mgr_create(const char* name, uint32_t num_workers, uint32_t ring_slots, ui
   off += static_cast<uint64_t>(payload_bytes) * num_workers;
   tmp.off_policy = off;
   off = align_up(off + sizeof(MgPolicy), 4096);
+  tmp.off_staged = off;
+  off += static_cast<uint64_t>(payload_bytes) * num_workers;
   tmp.total_bytes = off;
 
   shm_unlink(name);
@@ -462,7 +467,7 @@ int mgr_wait_assign(void* hv, uint32_t w, int64_t timeout_us, uint64_t* trial_id
     if (seq != c->ack_seq) {
       uint32_t n = c->assign_len;
       if (n > cap) return -1;
-      if (n) std::memcpy(buf, h->assign_buf(w), n);
+      if (n) std::memcpy(buf, c->assign_src ? h->staged_buf(w) : h->assign_buf(w), n);
       *len = n;
       *trial_id = c->assign_trial_id;
       store_rel(&c->ack_seq, seq);
@@ -476,8 +481,13 @@ int mgr_wait_assign(void* hv, uint32_t w, int64_t timeout_us, uint64_t* trial_id
       if (spent >= timeout_us) return 0;
       left = timeout_us - spent;
     }
-    // bounded sleep so a global stop / driver death is noticed even without a wake-up
-    int64_t nap = (left < 0 || left > 50000) ? 50000 : left;
+    // The scheduler kernel publishes a prefetched trial with a plain store from the GPU (nobody futex-wakes us):
+    // poll for the first 300 us after the call, nap briefly for the next 20 ms, then fall back to the bounded sleep
+    // that notices a global stop / driver death even without a wake-up.
+    const uint64_t waited = now_ns() - t0;
+    if (waited < 300000) continue;
+    int64_t cap_us = waited < 20000000 ? 200 : 50000;
+    int64_t nap = (left < 0 || left > cap_us) ? cap_us : left;
     futex_wait(&c->assign_seq, seq, nap);
     store_rel(&c->heartbeat_ns, now_ns());
   }
@@ -513,8 +523,53 @@ int mgr_assign_tagged(void* hv, uint32_t w, uint64_t trial_id, const void* data,
   c->assign_len = len;
   c->assign_trial_id = trial_id;
   c->assign_tag = tag;
+  c->assign_src = 0;
   store_rel(&c->stop_trial_id, static_cast<uint64_t>(0));
   store_rel(&c->assign_seq, c->assign_seq + 1);
+  futex_wake_all(&c->assign_seq);
+  return 0;
+}
+
+// Park the worker's NEXT trial in its staged area. -2: one is already parked. The entry stays valid until somebody
+// assigns something else to the worker (staged_seq == assign_seq + 1 no longer holds then).
+int mgr_stage(void* hv, uint32_t w, uint64_t trial_id, const void* data, uint32_t len, uint32_t tag) {
+  Handle* h = static_cast<Handle*>(hv);
+  MgHeader* hd = h->hdr();
+  if (w >= hd->num_workers || len > hd->payload_bytes) return -1;
+  MgWorkerCtl* c = h->ctl(w);
+  const uint32_t next = load_acq(&c->assign_seq) + 1;
+  if (load_acq(&c->staged_seq) == next) return -2;
+  if (len) std::memcpy(h->staged_buf(w), data, len);
+  c->staged_len = len;
+  c->staged_tag = tag;
+  c->staged_trial_id = trial_id;
+  store_rel(&c->staged_seq, next);
+  return 0;
+}
+
+// 1: a staged trial is parked and unpublished; 2: the worker's CURRENT assignment came out of the staged area;
+// 0: neither. `trial_id` receives the staged / published trial id for 1 / 2.
+int mgr_staged_state(void* hv, uint32_t w, uint64_t* trial_id) {
+  MgWorkerCtl* c = static_cast<Handle*>(hv)->ctl(w);
+  const uint32_t seq = load_acq(&c->assign_seq), st = load_acq(&c->staged_seq);
+  *trial_id = c->staged_trial_id;
+  if (st == seq + 1) return 1;
+  if (st == seq && c->assign_src == 1) return 2;
+  return 0;
+}
+
+// The driver-side publish of the parked trial (K9 does the same from the device: ring_device.cu publish_staged).
+int mgr_publish_staged(void* hv, uint32_t w) {
+  Handle* h = static_cast<Handle*>(hv);
+  MgWorkerCtl* c = h->ctl(w);
+  const uint32_t seq = load_acq(&c->assign_seq);
+  if (load_acq(&c->staged_seq) != seq + 1 || load_acq(&c->ack_seq) != seq) return -2;
+  c->assign_len = c->staged_len;
+  c->assign_trial_id = c->staged_trial_id;
+  c->assign_tag = c->staged_tag;
+  c->assign_src = 1;
+  store_rel(&c->stop_trial_id, static_cast<uint64_t>(0));
+  store_rel(&c->assign_seq, seq + 1);
   futex_wake_all(&c->assign_seq);
   return 0;
 }

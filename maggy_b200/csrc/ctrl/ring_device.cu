@@ -132,7 +132,7 @@ struct SchedArgs {
   unsigned long long* cursors;  // [num_workers][3]: host ring, host-mapped device ring, mailbox ring
   volatile unsigned int* quit;  // host-mapped: != 0 terminates the kernel
   unsigned long long* stats;    // [0] polls, [1] metrics seen, [2] stops issued, [3] finals seen, [4] mailbox records,
-                                // [5] next-trial (ASHA) decisions
+                                // [5] next-trial (ASHA) decisions, [6] prefetched trials handed off
   uint8_t* mailbox;             // device mailbox (local HBM) or nullptr
   unsigned int mbox_slots;
   long long gt_offset_ns;
@@ -281,6 +281,24 @@ sched_kernel(const SchedArgs a) {
                   __threadfence();
                   atomicExch(a.asha_lock, 0u);
                   done = true;
+                }
+              }
+              if (kind == MG_DEC_NEW) {
+                // prefetched hand-off (reference: the worker polls GET with sleep(1) until the driver has an answer,
+                // maggy/core/rpc.py:739-748): the driver parked this worker's next fresh configuration in the staged
+                // area; publishing it is five words and one release store — the worker is training again before the
+                // driver has even dequeued the FINAL message.
+                const unsigned int seq = ld_acquire_sys_u32(&ctl->assign_seq);
+                if (ld_acquire_sys_u32(&ctl->staged_seq) == seq + 1 && ld_acquire_sys_u32(&ctl->ack_seq) == seq) {
+                  ctl->assign_len = ctl->staged_len;
+                  ctl->assign_trial_id = ctl->staged_trial_id;
+                  ctl->assign_tag = ctl->staged_tag;
+                  ctl->assign_src = 1;
+                  st_release_sys_u64(reinterpret_cast<uint64_t*>(&ctl->stop_trial_id), 0ull);
+                  __threadfence_system();
+                  st_release_sys_u32(&ctl->assign_seq, seq + 1);
+                  kind = MG_DEC_NEW_PUBLISHED;
+                  atomicAdd(&a.stats[6], 1ull);
                 }
               }
               ctl->dec_kind = kind;

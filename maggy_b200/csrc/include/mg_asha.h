@@ -20,6 +20,7 @@ enum MgDecision : uint32_t {
   MG_DEC_NONE = 0,
   MG_DEC_NEW = 1,      // no promotable configuration: start a fresh one in rung 0
   MG_DEC_PROMOTE = 2,  // promote `parent` from rung `rung` to rung `rung + 1`
+  MG_DEC_NEW_PUBLISHED = 3,  // NEW, and the scheduler kernel already handed the worker its prefetched (staged) trial
 };
 
 struct MgAshaEntry {  // 32 bytes
@@ -36,7 +37,8 @@ struct MgAsha {
   uint32_t promoted[MG_ASHA_MAX_RUNGS];  // of which promoted
   uint32_t dropped;                      // finals that did not fit (cap exceeded)
   uint32_t decisions;
-  uint32_t pad[2];
+  uint32_t closed;                       // a configuration was promoted into the top rung: no further decisions
+  uint32_t pad;
   // MgAshaEntry entries[MG_ASHA_MAX_RUNGS][cap] follows
 };
 
@@ -75,6 +77,9 @@ MG_HD void mg_asha_record(MgAsha* a, uint32_t rung, uint64_t trial_id, double me
 // the promotion scan of asha.py:95-147. Returns the decision kind; for PROMOTE fills parent / rung and marks it.
 MG_HD uint32_t mg_asha_decide(MgAsha* a, uint64_t* parent, uint32_t* rung_out) {
   a->decisions += 1;
+  *parent = 0;
+  *rung_out = 0;
+  if (a->closed) return MG_DEC_NONE;  // asha.py:90-92: the experiment winds down once the top rung is populated
   for (int k = static_cast<int>(a->max_rung) - 1; k >= 0; --k) {
     const uint32_t quota = a->count[k] / a->rf;
     if (quota <= a->promoted[k]) continue;
@@ -85,11 +90,10 @@ MG_HD uint32_t mg_asha_decide(MgAsha* a, uint64_t* parent, uint32_t* rung_out) {
         a->promoted[k] += 1;
         *parent = e[i].trial_id;
         *rung_out = static_cast<uint32_t>(k);
+        if (static_cast<uint32_t>(k) + 1 >= a->max_rung) a->closed = 1;
         return MG_DEC_PROMOTE;
       }
     }
   }
-  *parent = 0;
-  *rung_out = 0;
   return MG_DEC_NEW;
 }

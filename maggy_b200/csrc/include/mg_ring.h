@@ -14,12 +14,13 @@
 //   GET/TRIAL -> driver writes the assign slot (+payload) and bumps assign_seq; worker futex-waits
 //   STOP  -> driver/policy writes ctl.stop_trial_id; GSTOP -> header.gstop
 //   BLACK -> heartbeat timeout / re-REG with a trial still assigned (handled by the driver)
+//   prefetched hand-off -> driver stages the next trial (mgr_stage); K9 publishes it on the worker's FINAL
 //   next-trial decision (ASHA rung scan) -> K9 writes ctl.dec_* when it sees a tagged FINAL (mg_asha.h)
 #pragma once
 #include <stdint.h>
 
 #define MG_RING_MAGIC 0x4d47523162323030ull /* "MGR1b200" */
-#define MG_RING_VERSION 4u
+#define MG_RING_VERSION 5u
 
 enum MgRecType : uint16_t {
   MG_REC_NONE = 0,
@@ -64,6 +65,14 @@ struct alignas(64) MgWorkerCtl {
   uint32_t stop_seq;                 // bumped with every stop request
   uint32_t assign_tag;               // opaque tag of the assigned trial (ASHA: rung + 1), echoed in its FINAL record
   uint64_t stop_t_ns;                // when the stop decision was taken (latency accounting)
+  // prefetched next trial: the driver parks a trial in the worker's STAGED payload area; whoever sees the worker's
+  // FINAL first (the scheduler kernel K9, else the driver) publishes it by copying the staged_* words over the
+  // assign_* words and storing assign_seq = staged_seq. Valid iff staged_seq == assign_seq + 1.
+  uint32_t assign_src;               // 0: payload sits in the assign area, 1: in the staged area
+  uint32_t staged_seq;
+  uint32_t staged_len;
+  uint32_t staged_tag;
+  uint64_t staged_trial_id;
   // ---- written by the worker
   alignas(64) uint64_t heartbeat_ns; // last sign of life
   uint32_t state;                    // MgWorkerState
@@ -117,6 +126,7 @@ struct alignas(64) MgHeader {
   uint64_t off_assign;       // per worker payload_bytes (driver -> worker)
   uint64_t off_blob;         // per worker payload_bytes (worker -> driver)
   uint64_t off_policy;       // MgPolicy + float table[cap_final][max_steps] + per-worker running state
+  uint64_t off_staged;       // per worker payload_bytes: the prefetched next trial (driver -> worker)
   uint64_t ring_stride;      // bytes between consecutive workers' rings
   alignas(64) uint32_t doorbell;   // bumped + futex-woken by host producers
   uint32_t gstop;                  // global stop

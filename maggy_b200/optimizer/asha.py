@@ -71,7 +71,7 @@ class Asha(AbstractOptimizer):
         return None
 
     # ---- device-side decisions (K9, csrc/include/mg_asha.h) ------------------------------------------------------
-    NEW, PROMOTE = 1, 2
+    NONE, NEW, PROMOTE, NEW_PUBLISHED = 0, 1, 2, 3
 
     def rung_of(self, trial) -> int:
         budget = trial.params.get("budget", self.resource_min)
@@ -99,6 +99,12 @@ class Asha(AbstractOptimizer):
             child = self._child_of(parent, rung)
             self._log(f"[device] promote {parent.trial_id} from rung {rung} to rung {rung + 1} as {child.trial_id}")
             return child
+        if kind != self.NEW:
+            return self.get_suggestion(trial)
+        return self.fresh_trial()
+
+    def fresh_trial(self):
+        """A new random configuration in rung 0 (also what the driver parks as a worker's prefetched next trial)."""
         params = self.searchspace.get_random_parameter_values(1)[0]
         params["budget"] = self.resource_min
         fresh = Trial(params, info_dict={"run_budget": self.resource_min, "sample_type": "random"})

@@ -222,3 +222,41 @@ def test_stop_latency_is_sub_millisecond(chan):
     lat.sort()
     assert lat[len(lat) // 2] < 5.0, lat   # ms; the reference needs 1-2 heartbeat periods (1-2 s)
     w.close()
+
+
+
+def test_prefetched_trial_is_parked_then_published():
+    """mgr_stage parks the worker's next trial; mgr_publish_staged (what K9 does from the GPU on the worker's FINAL)
+    hands it over without touching the payload; a direct assignment invalidates a parked entry."""
+    from maggy_b200.core import rpc
+
+    ch = rpc.DriverChannel(1, ring_slots=64, payload_bytes=1 << 16)
+    try:
+        w = rpc.WorkerChannel(ch.name, 0)
+        w.register()
+        assert any(m["type"] == "REG" for m in ch.next(0.5))
+        assert ch.assign(0, "00000000000000a1", {"params": {"lr": 0.1}}, tag=1)
+        assert ch.staged_state(0)[0] is None
+        assert ch.stage(0, "00000000000000b2", {"params": {"lr": 0.2}}, tag=1)
+        assert not ch.stage(0, "00000000000000c3", {"params": {"lr": 0.3}})          # slot taken
+        assert ch.staged_state(0) == ("parked", "00000000000000b2")
+        assert not ch.publish_staged(0)                                               # a1 not picked up yet
+        tid, payload = w.wait_assign(1.0)
+        assert tid == "00000000000000a1" and payload["params"]["lr"] == 0.1
+        w.post_final(tid, 0.5, {"metric": 0.5})
+        assert ch.publish_staged(0)
+        assert ch.staged_state(0) == ("published", "00000000000000b2")
+        tid, payload = w.wait_assign(1.0)
+        assert tid == "00000000000000b2" and payload["params"]["lr"] == 0.2
+        assert ch.reservations.get_assigned_trial(0) == "00000000000000b2"
+        finals = [m for m in ch.next(0.2) if m["type"] == "FINAL"]
+        assert finals and finals[0]["trial_id"] == "00000000000000a1"
+        # park again, then assign directly: the parked entry is void and can be re-parked
+        assert ch.stage(0, "00000000000000d4", {"params": {"lr": 0.4}})
+        assert ch.assign(0, "00000000000000e5", {"params": {"lr": 0.5}})
+        assert ch.staged_state(0)[0] is None and not ch.publish_staged(0)
+        assert w.wait_assign(1.0)[0] == "00000000000000e5"
+        assert ch.stage(0, "00000000000000d4", {"params": {"lr": 0.4}})
+        w.close()
+    finally:
+        ch.close()

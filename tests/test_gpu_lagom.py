@@ -144,6 +144,10 @@ def test_asha_rung_decisions_are_taken_by_the_device_scheduler(tmp_path, monkeyp
     assert k9["asha_decisions"] >= len(trials) - 1, (k9, len(trials))
     assert k9["asha_decisions_applied"] >= len(trials) - 2 and k9["asha_decision_fallbacks"] <= 1, k9
     assert k9["stops"] == 0
+    # prefetched hand-off: when the rung scan said "fresh configuration", K9 itself published the trial the driver had
+    # parked for that worker (most decisions of a rung-0-heavy ASHA run), and the driver adopted exactly those
+    assert k9["handoffs"] >= 3 and k9["prefetched_handoffs_adopted"] == k9["handoffs"], k9
+    assert "final_to_decision_ms_median" in k9
     # the promoted configurations are the ones the rung tables rank on top: parent of every budget-2 trial is in the
     # better half of the budget-1 trials finished so far (checked loosely: better than the rung's worst)
     worst_b1 = min(t["final_metric"] for t in trials if t["params"]["budget"] == 1)
