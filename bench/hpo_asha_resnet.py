@@ -170,6 +170,11 @@ def main():
         "inter_trial_gap_ms_max": None if not gaps else gaps[-1] * 1e3,
         "report_to_stop_latency_ms_median": None if not lats else med(lats) * 1e3,
         "proxy_reference_rpc": bool(args.proxy_reference_rpc),
+        "device_scheduler": (dict(d.device_scheduler_stats or {}, decisions_applied=d.device_decisions,
+                                  decision_fallbacks=d.device_decision_fallbacks, handoffs_adopted=d.device_handoffs,
+                                  final_to_decision_ms_median=(sorted(d.device_decision_latencies)[len(d.device_decision_latencies) // 2]
+                                                               if d.device_decision_latencies else None))
+                             if getattr(d, "device_scheduler_stats", None) else None),
         "config": {"model": args.model, "batch": args.batch, "image": image, "steps_per_budget": args.steps_per_budget,
                    "optimizer": "asha(rf=2, min=1, max=4)", "es_policy": args.es, "engine": args.engine},
     }

@@ -21,6 +21,8 @@ namespace {
 using namespace mg;
 
 constexpr int kUnroll = 4;
+constexpr int kPartCap = 296, kPartThreads = 512, kElemCap = 148 * 16;
+constexpr int kRowsPerWarp = (kPartCap + 31) / 32;  // partial rows one finalize warp sums
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
@@ -134,20 +136,21 @@ bn_fwd_finalize_kernel(const float* __restrict__ partial, int nparts, int C, dou
   const int c = blockIdx.x * 32 + lane;
   float s = 0.f, q = 0.f;
   if (c < C) {
-    float s2 = 0.f, q2 = 0.f;  // two rows in flight per warp: the loop is latency-bound
-    int p = warp;
-    for (; p + 32 < nparts; p += 64) {
-      s += partial[(static_cast<size_t>(p) * 2) * C + c];
-      q += partial[(static_cast<size_t>(p) * 2 + 1) * C + c];
-      s2 += partial[(static_cast<size_t>(p + 32) * 2) * C + c];
-      q2 += partial[(static_cast<size_t>(p + 32) * 2 + 1) * C + c];
+    // the kernel is one chain of memory latencies (9 us per launch in the ncu capture, 106 launches per ResNet step):
+    // issue every row this warp owns (<= kPartCap / 32) before summing any, so the chain is ONE round trip
+    float sv[kRowsPerWarp], qv[kRowsPerWarp];
+#pragma unroll
+    for (int k = 0; k < kRowsPerWarp; ++k) {
+      const int p = warp + 32 * k;
+      const bool ok = p < nparts;
+      sv[k] = ok ? partial[(static_cast<size_t>(p) * 2) * C + c] : 0.f;
+      qv[k] = ok ? partial[(static_cast<size_t>(p) * 2 + 1) * C + c] : 0.f;
     }
-    if (p < nparts) {
-      s += partial[(static_cast<size_t>(p) * 2) * C + c];
-      q += partial[(static_cast<size_t>(p) * 2 + 1) * C + c];
+#pragma unroll
+    for (int k = 0; k < kRowsPerWarp; ++k) {
+      s += sv[k];
+      q += qv[k];
     }
-    s += s2;
-    q += q2;
   }
   __shared__ float rs[32][33], rq[32][33];
   rs[warp][lane] = s;
@@ -293,20 +296,21 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int nparts, int C, flo
   const int c = blockIdx.x * 32 + lane;
   float s = 0.f, q = 0.f;
   if (c < C) {
-    float s2 = 0.f, q2 = 0.f;  // two rows in flight per warp: the loop is latency-bound
-    int p = warp;
-    for (; p + 32 < nparts; p += 64) {
-      s += partial[(static_cast<size_t>(p) * 2) * C + c];
-      q += partial[(static_cast<size_t>(p) * 2 + 1) * C + c];
-      s2 += partial[(static_cast<size_t>(p + 32) * 2) * C + c];
-      q2 += partial[(static_cast<size_t>(p + 32) * 2 + 1) * C + c];
+    // the kernel is one chain of memory latencies (9 us per launch in the ncu capture, 106 launches per ResNet step):
+    // issue every row this warp owns (<= kPartCap / 32) before summing any, so the chain is ONE round trip
+    float sv[kRowsPerWarp], qv[kRowsPerWarp];
+#pragma unroll
+    for (int k = 0; k < kRowsPerWarp; ++k) {
+      const int p = warp + 32 * k;
+      const bool ok = p < nparts;
+      sv[k] = ok ? partial[(static_cast<size_t>(p) * 2) * C + c] : 0.f;
+      qv[k] = ok ? partial[(static_cast<size_t>(p) * 2 + 1) * C + c] : 0.f;
     }
-    if (p < nparts) {
-      s += partial[(static_cast<size_t>(p) * 2) * C + c];
-      q += partial[(static_cast<size_t>(p) * 2 + 1) * C + c];
+#pragma unroll
+    for (int k = 0; k < kRowsPerWarp; ++k) {
+      s += sv[k];
+      q += qv[k];
     }
-    s += s2;
-    q += q2;
   }
   __shared__ float rs[32][33], rq[32][33];
   rs[warp][lane] = s;
@@ -397,7 +401,6 @@ int check() {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -400 - static_cast<int>(e);
 }
-constexpr int kPartCap = 296, kPartThreads = 512, kElemCap = 148 * 16;
 }  // namespace
 
 // fp32 scratch the partial-sum kernels need: kPartCap * 2 * C floats

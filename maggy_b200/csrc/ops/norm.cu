@@ -458,7 +458,7 @@ norm_bwd_kernel_v4(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
 
 // kAcc-row variant of the finalize kernel below for the v4 partial layout [nparts][nacc][C];
 // row 0 -> dgamma, row 1 -> dbeta (skipped when null), row 2 -> dcol (the producer's bias gradient)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 norm_bwd_finalize_v4_kernel(const float* __restrict__ partial, int nparts, int C, int nacc,
                             __nv_bfloat16* __restrict__ dgamma, __nv_bfloat16* __restrict__ dbeta,
                             __nv_bfloat16* __restrict__ dcol, int accumulate, int accumulate_col) {
@@ -466,15 +466,24 @@ norm_bwd_finalize_v4_kernel(const float* __restrict__ partial, int nparts, int C
   const int c = blockIdx.x * 32 + lane;  // column in [0, nacc * C)
   float acc = 0.f;
   if (c < nacc * C) {
-    for (int pidx = warp; pidx < nparts; pidx += 8) acc += partial[static_cast<size_t>(pidx) * nacc * C + c];
+    // one partial row per SM (<= 160): every row this warp owns is requested before any is summed — one round trip
+    float v[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int pidx = warp + 32 * k;
+      v[k] = pidx < nparts ? partial[static_cast<size_t>(pidx) * nacc * C + c] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc += v[k];
+    for (int pidx = warp + 160; pidx < nparts; pidx += 32) acc += partial[static_cast<size_t>(pidx) * nacc * C + c];
   }
-  __shared__ float red[8][33];
+  __shared__ float red[32][33];
   red[warp][lane] = acc;
   __syncthreads();
   if (warp == 0 && c < nacc * C) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    for (int w = 0; w < 32; ++w) t += red[w][lane];
     const int which = c / C, col = c - which * C;
     __nv_bfloat16* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dcol);
     const int accf = which == 2 ? accumulate_col : accumulate;
@@ -694,7 +703,7 @@ extern "C" int mg_norm_bwd_col(const void* dy, const void* x, const void* gamma,
 #undef MG_V4
   if (rc) return rc;
   const int nacc = col ? 3 : 2;
-  norm_bwd_finalize_v4_kernel<<<(nacc * C + 31) / 32, 256, 0, s>>>(
+  norm_bwd_finalize_v4_kernel<<<(nacc * C + 31) / 32, 1024, 0, s>>>(
       partial, grid, C, nacc, reinterpret_cast<__nv_bfloat16*>(dgamma),
       rms ? nullptr : reinterpret_cast<__nv_bfloat16*>(dbeta), reinterpret_cast<__nv_bfloat16*>(dcol), accumulate,
       accumulate_col);
