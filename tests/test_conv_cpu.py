@@ -91,3 +91,24 @@ def test_fused_batchnorm_module_falls_back_on_cpu():
     x, r = torch.randn(4, 8, 5, 5), torch.randn(4, 8, 5, 5)
     assert torch.allclose(bn(x, r), torch.relu(ref(x) + r), atol=1e-6)
     assert torch.allclose(bn.running_var, ref.running_var)
+
+
+def test_native_pool_and_skip_conv_fall_back_on_cpu():
+    """ops.pool.MaxPool2d and Conv2d(..., with_skip=True) on CPU tensors: plain ATen results, same call signatures as on
+    the GPU (ResNet bottlenecks use both on every device)."""
+    import torch
+
+    from maggy_b200.models.resnet import resnet18ish
+    from maggy_b200.ops.conv import Conv2d
+    from maggy_b200.ops.pool import MaxPool2d
+
+    torch.manual_seed(0)
+    x = torch.randn(2, 8, 9, 9)
+    assert torch.equal(MaxPool2d(3, stride=2, padding=1)(x), torch.nn.MaxPool2d(3, stride=2, padding=1)(x))
+    conv = Conv2d(8, 16, 1, dtype=torch.float32)
+    y, skip = conv(x, with_skip=True)
+    assert skip is x and torch.equal(y, conv(x))
+    net = resnet18ish(10)
+    out = net(torch.randn(2, 3, 32, 32))
+    out.sum().backward()
+    assert out.shape == (2, 10) and net.conv1.weight.grad is not None
