@@ -28,7 +28,7 @@ class BertConfig:
 
     @classmethod
     def named(cls, name: str) -> "BertConfig":
-        table = {"bert-base": dict(), "bert-tiny": dict(vocab_size=1000, hidden=128, n_layers=2, n_heads=4, ffn=256, max_pos=128)}
+        table = {"bert-base": dict(), "bert-tiny": dict(vocab_size=1000, hidden=128, n_layers=2, n_heads=2, ffn=256, max_pos=128)}
         return cls(**table[name])
 
 

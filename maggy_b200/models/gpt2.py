@@ -38,7 +38,8 @@ class GPT2Config:
     @classmethod
     def named(cls, name: str) -> "GPT2Config":
         table = {
-            "gpt2-tiny": dict(n_layer=2, n_head=4, n_embd=128, block_size=128, vocab_size=1000),
+            # head_dim 64 like every real GPT-2 size: the tiny config runs the native attention kernels too
+            "gpt2-tiny": dict(n_layer=2, n_head=2, n_embd=128, block_size=128, vocab_size=1000),
             "gpt2-small": dict(n_layer=12, n_head=12, n_embd=768),
             "gpt2-medium": dict(n_layer=24, n_head=16, n_embd=1024),
             "gpt2-large": dict(n_layer=36, n_head=20, n_embd=1280),
@@ -93,6 +94,13 @@ class Block(nn.Module):
         if self.attn_impl == "native" and C // H == 64 and qkv.is_cuda:
             # K10: reads q/k/v straight out of the fused projection, writes [B, T, C]; no split / transpose / cat
             y = F.attention(qkv, H, causal=True)
+        elif self.attn_impl == "math":
+            # unfused reference arm (matmul, mask, softmax, matmul): what the tests compare the kernels against
+            q, k, v = (t.transpose(1, 2) for t in qkv.view(B, T, 3, H, C // H).unbind(dim=2))
+            att = (q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(C // H))
+            mask = torch.ones(T, T, dtype=torch.bool, device=x.device).tril()
+            att = att.masked_fill(~mask, float("-inf")).float().softmax(dim=-1).to(q.dtype)
+            y = (att @ v).transpose(1, 2).reshape(B, T, C)
         else:
             q, k, v = qkv.view(B, T, 3, H, C // H).unbind(dim=2)
             y = torch.nn.functional.scaled_dot_product_attention(
@@ -176,10 +184,13 @@ class TorchGPT2(nn.Module):
         for b in m.blocks:
             h = tf.layer_norm(x, (C,), b.ln1_w, b.ln1_b, cfg.layer_norm_eps)
             qkv = tf.linear(h, b.qkv_w, b.qkv_b).view(B, T, 3, H, C // H)
-            q, k, v = qkv.unbind(dim=2)
-            y = tf.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
-                                                is_causal=True)
-            y = y.transpose(1, 2).reshape(B, T, C)
+            q, k, v = (t.transpose(1, 2) for t in qkv.unbind(dim=2))
+            # written out (matmul, mask, softmax, matmul) instead of F.scaled_dot_product_attention: the oracle must not
+            # depend on a fused library attention kernel either
+            att = (q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(C // H))
+            mask = torch.ones(T, T, dtype=torch.bool, device=x.device).tril()
+            att = att.masked_fill(~mask, float("-inf")).float().softmax(dim=-1).to(q.dtype)
+            y = (att @ v).transpose(1, 2).reshape(B, T, C)
             x = x + tf.linear(y, b.proj_w, b.proj_b)
             h = tf.layer_norm(x, (C,), b.ln2_w, b.ln2_b, cfg.layer_norm_eps)
             x = x + tf.linear(tf.gelu(tf.linear(h, b.fc_w, b.fc_b), approximate="tanh"), b.fc2_w, b.fc2_b)

@@ -35,7 +35,7 @@ class LlamaConfig:
     def named(cls, name: str) -> "LlamaConfig":
         table = {
             "llama3-1b": dict(),
-            "llama-tiny": dict(vocab_size=1024, dim=128, n_layers=2, n_heads=4, n_kv_heads=2, ffn_dim=256, max_seq_len=128),
+            "llama-tiny": dict(vocab_size=1024, dim=128, n_layers=2, n_heads=2, n_kv_heads=1, ffn_dim=256, max_seq_len=128),
             # small enough for tests, wide enough to shard over 2 or 4 ranks (rows per shard stay multiples of 128)
             "llama-small": dict(vocab_size=4096, dim=512, n_layers=4, n_heads=8, n_kv_heads=4, ffn_dim=1024,
                                 max_seq_len=512),

@@ -71,7 +71,7 @@ def test_attention_bwd(case):
     assert _rel(g[..., Cq + Ckv:], g_ref[..., Cq + Ckv:]) < 2e-2, "dV"
 
 
-def test_gpt2_native_attention_matches_sdpa():
+def test_gpt2_native_attention_matches_unfused_math():
     from maggy_b200.models.gpt2 import GPT2, GPT2Config
 
     torch.manual_seed(5)
@@ -79,7 +79,7 @@ def test_gpt2_native_attention_matches_sdpa():
     model = GPT2(cfg).cuda().to(torch.bfloat16)
     idx = torch.randint(0, 1000, (4, 256), device="cuda")
     losses, grads = [], []
-    for impl in ("sdpa", "native"):
+    for impl in ("math", "native"):
         for blk in model.blocks:
             blk.attn_impl = impl
         model.zero_grad(set_to_none=True)
