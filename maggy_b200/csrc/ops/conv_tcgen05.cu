@@ -744,7 +744,27 @@ int mg_conv2d_fprop(const void* x, const void* w, void* y, int N, int H, int W, 
   fill_geometry(p, N, H, W, C, Kout, R, S, pad_h, pad_w);
   if (p.P <= 0 || p.Q <= 0) return -2;
   p.relu = relu;
-  const int block_n = (Kout % 256 == 0) ? 256 : (Kout % 128 == 0 ? 128 : 64);
+  int max_ctas = num_sms();
+  if (sm_limit > 0 && sm_limit < max_ctas) max_ctas = sm_limit;
+  // Output-channel tile width by a wave model: cost = waves * (k-blocks * max(bn, 128) + fixed). A 64-wide tile costs as
+  // much per k-block as a 128-wide one (the A operand's shared-memory reads bound it), and a small pixel count with
+  // 256-wide tiles leaves SMs idle: the 7x7 layers of ResNet-50 (25 pixel tiles x 512 channels) fill 50 SMs with
+  // bn = 256 and 100 with bn = 128 at half the time per tile.
+  int block_n = 64;
+  {
+    const long long kblocks = static_cast<long long>(R) * S * (C / 64);
+    double best = 0.0;
+    for (int bn : {256, 128, 64}) {
+      if (Kout % bn != 0) continue;
+      const long long tiles = static_cast<long long>(p.num_m_tiles) * (Kout / bn);
+      const long long waves = (tiles + max_ctas - 1) / max_ctas;
+      const double cost = static_cast<double>(waves) * (static_cast<double>(kblocks) * (bn > 128 ? bn : 128) + 1500.0);
+      if (best == 0.0 || cost < best * 0.97) {
+        best = cost;
+        block_n = bn;
+      }
+    }
+  }
   p.num_n_blocks = Kout / block_n;
   CUtensorMap mx, mw, my;
   int rc = make_map_nhwc(&mx, x, N, H, W, C, p.bw, p.bh, p.bn);
@@ -753,8 +773,6 @@ int mg_conv2d_fprop(const void* x, const void* w, void* y, int N, int H, int W, 
   if (rc) return rc;
   rc = make_map_nhwc(&my, y, N, p.P, p.Q, Kout, p.bw, p.bh, p.bn);
   if (rc) return rc;
-  int max_ctas = num_sms();
-  if (sm_limit > 0 && sm_limit < max_ctas) max_ctas = sm_limit;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (block_n == 256) return launch_fprop<256, 4>(mx, mw, my, p, max_ctas, s);
   if (block_n == 128) return launch_fprop<128, 6>(mx, mw, my, p, max_ctas, s);

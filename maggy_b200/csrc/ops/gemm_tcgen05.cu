@@ -708,7 +708,7 @@ int num_sms() {
   return g_num_sms;
 }
 
-int pick_block_n(int M, int N) {
+int pick_block_n(int M, int N, int K = 0) {
   // Wide tiles have the best arithmetic intensity per byte of smem/L2 traffic, so 128-wide tiles are only
   // for narrow outputs. Between 256 and 192 pick the one that wastes less of the last wave of the
   // persistent grid (e.g. M=32768, N=768: 768 tiles of 256 = 5.2 waves -> 6; 1024 tiles of 192 = 6.9 -> 7,
@@ -725,6 +725,12 @@ int pick_block_n(int M, int N) {
   // Measured on B200 (profiles/gemm_bench_*.log): 192-wide tiles lose more to their lower arithmetic
   // intensity (L2 -> smem traffic per FLOP) than they gain from the better last wave, even at N = 768, so
   // 256 stays the default and 192 is only taken when it saves more than a quarter of the work units.
+  // Under-filled grids (few row blocks, e.g. the 7x7 layers of ResNet-50: 25 row blocks x 512 columns = 50 tiles on
+  // 148 SMs): 128-wide tiles double the tile count at half the time per tile. Taken only when that saves more than a
+  // quarter of the wave-time, so the large training GEMMs (hundreds of row blocks) keep their 256-wide tiles.
+  // Long reductions are excluded: there split-K over 256-wide CTA-pair tiles fills the chip with better operand reuse
+  // (the GPT-2 weight gradients lost 8 % end to end when this rule caught them).
+  if (K > 0 && K < 4096 && cost(128) * 4 < cost(256) * 3 && cost(128) * 4 < cost(192) * 3) return 128;
   return cost(192) * 4 < cost(256) * 3 ? 192 : 256;
 }
 
@@ -733,7 +739,7 @@ int pick_block_n(int M, int N) {
 // How many K-splits mg_gemm_bf16 will use for (M, N, K) when asked for `splits == 0` (auto): the caller
 // needs it to size the fp32 workspace (splits * M * N floats). 1 means no split-K.
 extern "C" int mg_gemm_auto_splits(int M, int N, int K, int block_n) {
-  if (block_n == 0) block_n = pick_block_n(M, N);
+  if (block_n == 0) block_n = pick_block_n(M, N, K);
   const long long m_blocks = (M + BLOCK_M - 1) / BLOCK_M, n_blocks = (N + block_n - 1) / block_n;
   long long tiles = m_blocks * n_blocks;
   int kb = (K + BLOCK_K - 1) / BLOCK_K;
@@ -783,7 +789,7 @@ extern "C" int mg_gemm_bf16(const void* A, const void* B, void* C, const void* b
                             void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((N % 8) != 0 || (lda % 8) != 0 || (ldb % 8) != 0 || (ldc % (out_f32 ? 4 : 8)) != 0) return -1;
-  if (block_n == 0) block_n = pick_block_n(M, N);
+  if (block_n == 0) block_n = pick_block_n(M, N, K);
   if (splits < 1) splits = 1;
   if (splits > 1 && (epi != EPI_NONE || ws == nullptr || ldc != N)) return -3;
   GemmParams p;
