@@ -534,6 +534,39 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   }
 }
 
+// out[i] (+)= sum_s ws[s][i], one thread per output vector walking the splits: the right shape for FEW splits over a
+// LARGE output (GPT-2 weight gradients: 2-8 splits x 0.6-2.4 M floats; the split-lane kernel below took 2.5x longer there)
+__global__ void __launch_bounds__(256)
+splitk_reduce_flat_kernel(const float* __restrict__ ws, int splits, long long n, void* __restrict__ out,
+                          int out_f32, int accumulate) {
+  pdl_prologue();
+  const long long nvec = n >> 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 acc = reinterpret_cast<const float4*>(ws)[i];
+    for (int s = 1; s < splits; ++s) {
+      const float4 t = reinterpret_cast<const float4*>(ws + static_cast<long long>(s) * n)[i];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    if (out_f32) {
+      float4* o = reinterpret_cast<float4*>(out) + i;
+      if (accumulate) {
+        const float4 t = *o;
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+      *o = acc;
+    } else {
+      uint2* o = reinterpret_cast<uint2*>(out) + i;
+      if (accumulate) {
+        const uint2 t = *o;
+        const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y);
+        acc.x += a.x; acc.y += a.y; acc.z += b.x; acc.w += b.y;
+      }
+      *o = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+    }
+  }
+}
+
 // out[i] (+)= sum_s ws[s][i]   (split-K second pass; n multiple of 4). A CTA is 32 output vectors x 8 split lanes:
 // lane y sums splits y, y+8, ... (up to four loads in flight), the eight partial sums meet in shared memory. With one
 // split per SM (thin weight gradients: up to 148 partials) a single thread walking all the splits was a chain of
@@ -858,10 +891,16 @@ extern "C" int mg_gemm_bf16(const void* A, const void* B, void* C, const void* b
   if (p.splits > 1) {
     long long n = static_cast<long long>(M) * N;
     long long nvec = n >> 2;
-    long long blocks = (nvec + 31) / 32;
-    int grid = static_cast<int>(blocks < 148LL * 32 ? blocks : 148LL * 32);
-    cudaError_t e = launch_pdl(splitk_reduce_kernel, dim3(grid), dim3(256), 0, s, 1, ws, p.splits, n, C, out_f32,
-                               accumulate);
+    cudaError_t e;
+    if (p.splits <= 8) {
+      long long blocks = (nvec + 255) / 256;
+      int grid = static_cast<int>(blocks < 148LL * 8 ? blocks : 148LL * 8);
+      e = launch_pdl(splitk_reduce_flat_kernel, dim3(grid), dim3(256), 0, s, 1, ws, p.splits, n, C, out_f32, accumulate);
+    } else {
+      long long blocks = (nvec + 31) / 32;
+      int grid = static_cast<int>(blocks < 148LL * 32 ? blocks : 148LL * 32);
+      e = launch_pdl(splitk_reduce_kernel, dim3(grid), dim3(256), 0, s, 1, ws, p.splits, n, C, out_f32, accumulate);
+    }
     if (e != cudaSuccess) return -500 - static_cast<int>(e);
   }
   return 0;

@@ -124,3 +124,36 @@ def test_maxpool_matches_aten_including_relu_ties(shape, k, s, p):
     y2.backward(g)
     assert _rel(x1.grad, x2.grad) < 4e-3   # overlapping windows: ATen sums in fp32 atomics, here fp32 then one rounding
     assert torch.equal(x1.grad == 0, x2.grad == 0)
+
+
+@pytest.mark.parametrize("relu,res", [(True, True), (False, False)])
+def test_batchnorm_frozen_statistics_backward(relu, res):
+    """eval() mode with gradients (frozen-BN fine-tuning): y uses the running statistics, dx = gamma / std * dz and
+    dgamma / dbeta are still produced."""
+    from maggy_b200.ops.batchnorm import BatchNorm2d
+
+    torch.manual_seed(2)
+    shape = (4, 64, 12, 12)
+    x = (torch.randn(shape, device="cuda") * 1.3 + 0.2).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    r = torch.randn(shape, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last) if res else None
+    g = torch.randn(shape, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    bn, ref = BatchNorm2d(64, relu=relu).cuda(), torch.nn.BatchNorm2d(64).cuda()
+    with torch.no_grad():
+        for m in (bn, ref):
+            m.running_mean.copy_(torch.linspace(-0.5, 0.5, 64))
+            m.running_var.copy_(torch.linspace(0.5, 2.0, 64))
+            m.weight.copy_(torch.linspace(0.5, 1.5, 64))
+            m.bias.copy_(torch.linspace(-0.2, 0.2, 64))
+    bn.eval(), ref.eval()
+    x1 = x.clone().requires_grad_(True)
+    r1 = r.clone().requires_grad_(True) if res else None
+    bn(x1, r1).backward(g)
+    x2 = x.float().requires_grad_(True)
+    r2 = r.float().requires_grad_(True) if res else None
+    o = ref(x2) + (r2 if res else 0)
+    (torch.relu(o) if relu else o).backward(g.float())
+    assert _rel(x1.grad, x2.grad) < 1e-2
+    assert _rel(bn.weight.grad, ref.weight.grad) < 2e-2 and _rel(bn.bias.grad, ref.bias.grad) < 2e-2
+    if res:
+        assert _rel(r1.grad, r2.grad) < 1e-2
+    assert torch.equal(bn.running_mean, ref.running_mean)      # untouched
