@@ -1,6 +1,7 @@
 """Dump, per kernel of libmaggy_b200_cuda.so, the SASS mnemonics that prove the Blackwell-native path
 (UTC*MMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG/UTMASTG = TMA, SYNCS = mbarrier, LDGMC/multimem, .SYS
-release/acquire). Writes profiles/sass_summary.txt. Runs without a GPU."""
+release/acquire, ACQBULK / PREEXIT = griddepcontrol.wait / launch_dependents, UBLKCP = cp.async.bulk, UTMAREDG = TMA
+reduce). Writes profiles/sass_summary.txt. Runs without a GPU."""
 import collections
 import os
 import re
@@ -12,7 +13,7 @@ LIB = os.path.join(ROOT, "maggy_b200", "lib", "libmaggy_b200_cuda.so")
 PAT = re.compile(r"\b(UTC[A-Z]*MMA[A-Z0-9_.]*|UTCBAR[A-Z0-9_.]*|UTCATOMSWS[A-Z0-9_.]*|LDTM[A-Z0-9_.]*|UTMALDG[A-Z0-9_.]*|"
                  r"UTMASTG[A-Z0-9_.]*|UTMAPF[A-Z0-9_.]*|UBLKCP[A-Z0-9_.]*|SYNCS[A-Z0-9_.]*|LDGMC[A-Z0-9_.]*|"
                  r"STG?[A-Z0-9_.]*MC[A-Z0-9_.]*|HMMA[A-Z0-9_.]*|LDG\.E[A-Z0-9_.]*SYS|STG\.E[A-Z0-9_.]*SYS|"
-                 r"REDG?\.E[A-Z0-9_.]*SYS|FENCE[A-Z0-9_.]*|NANOSLEEP[A-Z0-9_.]*)")
+                 r"REDG?\.E[A-Z0-9_.]*SYS|FENCE[A-Z0-9_.]*|NANOSLEEP[A-Z0-9_.]*|ACQBULK[A-Z0-9_.]*|PREEXIT[A-Z0-9_.]*|UTMAREDG[A-Z0-9_.]*|UTCCP[A-Z0-9_.]*|UTCQMMA[A-Z0-9_.]*)")
 
 
 def main():
