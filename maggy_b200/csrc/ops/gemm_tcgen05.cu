@@ -34,7 +34,8 @@ enum Epi : int {
   EPI_NONE = 0,
   EPI_BIAS = 1,           // out = acc + bias[n]
   EPI_BIAS_GELU = 2,      // aux = acc + bias[n]; out = gelu(aux)
-  EPI_DGELU = 3,          // out = acc * gelu'(aux[m,n])
+  EPI_DGELU = 3,          // out = acc * gelu'(aux[m,n]); a non-null `bias` is an fp32 [4 * m_blocks][N] buffer that
+                          // receives the column sums of `out` per 32-row warp slice (the bias gradient, see below)
   EPI_BIAS_RESIDUAL = 4,  // out = acc + bias[n] + aux[m,n]
 };
 
@@ -332,6 +333,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         const bool has_bias = p.bias != nullptr && (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU ||
                                                     p.epi == EPI_BIAS_RESIDUAL);
         const bool reads_aux = p.epi == EPI_DGELU || p.epi == EPI_BIAS_RESIDUAL;
+        // dGELU + bias gradient: the tile this warp stages for the TMA store is read back column-wise (32 rows x 2
+        // columns per lane, conflict-free under the 128-byte swizzle) and the sums go to row (4 * m_blk + q) of the
+        // partial buffer — the separate column-sum pass over d_pre (2 x 400 MB per GPT-2 layer) disappears.
+        float* cs_row = (p.epi == EPI_DGELU && p.bias != nullptr)
+                            ? reinterpret_cast<float*>(const_cast<__nv_bfloat16*>(p.bias)) +
+                                  static_cast<long long>(m_blk * 4 + q) * p.N
+                            : nullptr;
         const __nv_bfloat16* aux_row = p.aux + static_cast<long long>(row) * p.ld_aux;
         uint4 aux_cur[8], aux_nxt[8];
         if (reads_aux && row_ok) {
@@ -403,6 +411,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
             if (lane == 0) {
               tma_store_2d(map, out_stage + obuf * 4096, col0, row0);
               tma_store_commit();
+            }
+            if (cs_row != nullptr && map == &tma_c) {
+              const uint8_t* base = out_stage + obuf * 4096;
+              const int rows_valid = p.M - row0;  // rows past M hold whatever gelu'(unloaded aux) produced: skip them
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) {
+                if (r < rows_valid) {
+                  const uint32_t w = *reinterpret_cast<const uint32_t*>(
+                      base + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+                  const float2 f = unpack_bf16x2(w);
+                  s0 += f.x;
+                  s1 += f.y;
+                }
+              }
+              if (col0 + 2 * lane + 2 <= p.N) *reinterpret_cast<float2*>(cs_row + col0 + 2 * lane) = make_float2(s0, s1);
             }
             obuf ^= 1;
           };
@@ -843,6 +867,7 @@ extern "C" int mg_gemm_bf16(const void* A, const void* B, void* C, const void* b
   p.scale_a = nullptr;
   p.scale_b = nullptr;
   p.tma_store = (!out_f32 && !accumulate && p.splits == 1) ? 1 : 0;
+  if (epi == EPI_DGELU && bias != nullptr && !p.tma_store) return -5;  // column sums exist on the staged path only
 
   Maps m;
   int rc;

@@ -446,6 +446,45 @@ extern "C" int mg_ce_fwd_bwd(void* logits, const long long* targets, float* loss
   return check();
 }
 
+// many partial rows (the GEMM epilogue writes one per 32-row warp slice): 32 warps per CTA, eight rows requested per
+// warp before any is summed, so 2048 rows are eight round trips instead of a 256-deep latency chain
+__global__ void __launch_bounds__(1024)
+colsum_finalize_wide_kernel(const float* __restrict__ partial, int nslabs, int N, __nv_bfloat16* __restrict__ out,
+                            int accumulate) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (n < N) {
+    int i = warp;
+    for (; i + 7 * 32 < nslabs; i += 8 * 32) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = partial[static_cast<size_t>(i + 32 * k) * N + n];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[k];
+    }
+    for (; i < nslabs; i += 32) s += partial[static_cast<size_t>(i) * N + n];
+  }
+  __shared__ float red[32][33];
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll 8
+    for (int w = 0; w < 32; ++w) t += red[w][lane];
+    if (accumulate) t += __bfloat162float(out[n]);
+    out[n] = __float2bfloat16(t);
+  }
+}
+
+// out[n] (+)= sum over `nslabs` rows of an fp32 partial buffer [nslabs][N] (written by the dGELU GEMM epilogue)
+extern "C" int mg_colsum_finalize(const float* partial, int nslabs, int N, void* out, int accumulate, void* stream) {
+  if (nslabs <= 0 || N <= 0) return -1;
+  colsum_finalize_wide_kernel<<<(N + 31) / 32, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      partial, nslabs, N, reinterpret_cast<__nv_bfloat16*>(out), accumulate);
+  return check();
+}
+
 extern "C" int mg_colsum_slabs(int M) {
   int s = (M + 127) / 128;  // >= 128 rows per slab keeps the 4-deep load loop busy
   return s < 1 ? 1 : (s > 256 ? 256 : s);

@@ -63,6 +63,7 @@ def cuda():
         _sig(lib.mg_attn_fwd, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P])
         _sig(lib.mg_attn_bwd, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P])
         _sig(lib.mg_set_device, [c_int])
+        _sig(lib.mg_colsum_finalize, [P, c_int, c_int, P, c_int, P])
         _sig(lib.mg_norm_fwd, [P, P, P, P, P, P, c_int, c_int, c_float, c_int, P])
         _sig(lib.mg_norm_bwd_grid, [c_int])
         _sig(lib.mg_norm_bwd, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P])

@@ -24,6 +24,10 @@ import torch
 from . import _lib
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_BIAS_RESIDUAL = 0, 1, 2, 3, 4
+# Column sums of d_pre inside the dGELU dgrad epilogue: correct (tests) but measured SLOWER end to end on the same box
+# (GPT-2 small, B = 64: 990.3 k / 984.2 k tokens/s without vs 979.0 k / 975.9 k with) — that GEMM's epilogue is already
+# its critical path and the read-back adds 128 LDS + 256 FADD per thread per tile. Off by default, kept for the record.
+_DGELU_COLSUM = __import__("os").environ.get("MAGGY_B200_DGELU_COLSUM", "0") != "0"
 K_MAJOR, MN_MAJOR = 0, 1
 
 _scratch: dict = {}
@@ -92,7 +96,11 @@ def gemm(a, b, *, a_major=K_MAJOR, b_major=K_MAJOR, bias=None, aux=None, epi=EPI
     if epi in (EPI_BIAS_GELU, EPI_DGELU, EPI_BIAS_RESIDUAL):
         assert aux is not None and aux.shape == (M, N) and aux.stride(1) == 1 and aux.dtype == torch.bfloat16
         ld_aux = aux.stride(0)
-    if bias is not None:
+    if bias is not None and epi == EPI_DGELU:
+        # not a bias: the fp32 buffer that receives the column sums of the output per 32-row slice (see _MLP.backward)
+        assert bias.dtype == torch.float32 and bias.numel() >= 4 * ((M + 127) // 128) * N and bias.is_contiguous()
+        assert out.dtype == torch.bfloat16 and not accumulate
+    elif bias is not None:
         assert bias.dtype == torch.bfloat16 and bias.numel() == N and bias.is_contiguous()
     lib = _lib.cuda()
     stream = _stream()
@@ -576,8 +584,13 @@ class _MLP(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        # d_pre = (dy W2) * gelu'(pre): dGELU fused into the dgrad epilogue
-        dpre = gemm(dy2, w2, b_major=MN_MAJOR, aux=pre, epi=EPI_DGELU)
+        # d_pre = (dy W2) * gelu'(pre): dGELU fused into the dgrad epilogue — which also leaves the column sums of d_pre
+        # (= the fc bias gradient) behind as fp32 partial rows, one per 32-row warp slice of the output
+        M_, N1 = dy2.shape[0], w2.shape[1]
+        fuse_db1 = b1 is not None and _DGELU_COLSUM and N1 % 8 == 0
+        cs_rows = 4 * ((M_ + 127) // 128)
+        cs_part = _scratch_f32("dgelu_colsum", cs_rows * N1, dy2.device) if fuse_db1 else None
+        dpre = gemm(dy2, w2, b_major=MN_MAJOR, aux=pre, epi=EPI_DGELU, bias=cs_part)
         dw2 = _write_or_return_grad(
             w2, lambda dst, acc: gemm(dy2, act, a_major=MN_MAJOR, b_major=MN_MAJOR, out=dst, accumulate=acc))
         db2 = None
@@ -586,7 +599,15 @@ class _MLP(torch.autograd.Function):
         dx = gemm(dpre, w1, b_major=MN_MAJOR).view(ctx.xshape)
         dw1 = _write_or_return_grad(
             w1, lambda dst, acc: gemm(dpre, x2, a_major=MN_MAJOR, b_major=MN_MAJOR, out=dst, accumulate=acc))
-        db1 = _write_or_return_grad(b1, lambda dst, acc: colsum(dpre, dst, accumulate=acc))
+        if fuse_db1:
+            def _finalize(dst, acc):
+                _lib.check(_lib.cuda().mg_colsum_finalize(cs_part.data_ptr(), cs_rows, N1, dst.data_ptr(),
+                                                          1 if acc else 0, _stream()), "mg_colsum_finalize")
+                _count(1)
+
+            db1 = _write_or_return_grad(b1, _finalize)
+        else:
+            db1 = _write_or_return_grad(b1, lambda dst, acc: colsum(dpre, dst, accumulate=acc))
         return dx, dw1, db1, dw2, db2, (dy if ctx.has_res else None)
 
 
