@@ -465,3 +465,79 @@ def test_driver_survives_poisoned_records():
     res = experiment.lagom(train_with_poisoned_records, cfg)
     assert res["num_trials"] == 4 and len(res["metric_list"]) == 4
     assert all(0.0 <= m <= 1.0 for m in res["metric_list"])                  # the 1e9 / 5.0 garbage never became a result
+
+
+def test_asha_with_a_stand_in_for_the_device_scheduler(monkeypatch):
+    """The driver side of the device-scheduler protocol, on CPU: a stand-in plays K9 with the SAME rung-table code
+    (mg_asha.h through the host library) — it files every tagged FINAL, decides promote / fresh, and publishes the
+    parked trial itself when the answer is "fresh" (mgr_publish_staged = what the kernel does with five stores). The
+    driver must adopt the hand-offs, apply the promotions, keep parking prefetched trials and finish the experiment with
+    the same artefacts as the host-decided run."""
+    import ctypes
+
+    from maggy_b200.core import rpc
+    from maggy_b200.core.drivers.optimization_driver import HyperparameterOptDriver
+    from maggy_b200.optimizer import Asha
+
+    lib = rpc._host()
+    state = {}
+
+    def fake_start(self):      # instead of launching the CUDA kernel
+        c = self.controller
+        state["tab"] = lib.mgr_asha_create(c.reduction_factor, c.max_rung, 256, 1 if self.direction == "max" else -1)
+        state["dec"], state["seq"] = {}, {}
+        self._device_asha = True
+
+    orig_final = HyperparameterOptDriver._final_msg_callback
+
+    def final_with_k9(self, msg):   # "K9" sees the FINAL record before the driver's digest thread handles the message
+        trial = self.get_trial(msg["trial_id"])
+        if trial is not None and getattr(trial, "_device_tagged", False):
+            w = msg["partition_id"]
+            parent, rung = ctypes.c_uint64(), ctypes.c_uint32()
+            metric = (msg["data"] or {}).get("metric", msg["value"])
+            kind = lib.mgr_asha_final(state["tab"], self.controller.rung_of(trial), int(trial.trial_id, 16), float(metric),
+                                      ctypes.byref(parent), ctypes.byref(rung))
+            if kind == Asha.NEW and self.channel.staged_state(w)[0] == "parked" and self.channel.publish_staged(w):
+                kind = Asha.NEW_PUBLISHED
+            state["seq"][w] = state["seq"].get(w, 0) + 1
+            state["dec"][(w, state["seq"][w])] = (kind, rung.value, f"{parent.value:016x}", msg["t_ns"] + 1000)
+        return orig_final(self, msg)
+
+    monkeypatch.setattr(HyperparameterOptDriver, "_start_device_scheduler", fake_start)
+    monkeypatch.setattr(HyperparameterOptDriver, "_final_msg_callback", final_with_k9)
+    monkeypatch.setattr(rpc.DriverChannel, "device_decision",
+                        lambda self, worker, expected, timeout_s=0.002: state["dec"].get((worker, expected)))
+    holder = {}
+    orig_json = HyperparameterOptDriver.json
+
+    def spy_json(self):
+        holder["d"] = self
+        return orig_json(self)
+
+    monkeypatch.setattr(HyperparameterOptDriver, "json", spy_json)
+
+    def train(hparams, reporter):
+        for i in range(int(hparams["budget"])):
+            reporter.broadcast(1.0 - abs(hparams["lr"] - 0.3), i)
+        return 1.0 - abs(hparams["lr"] - 0.3)
+
+    sp = Searchspace(lr=("DOUBLE", [0.0, 1.0]))
+    res = experiment.lagom(train, HyperparameterOptConfig(num_trials=24, optimizer=Asha(2, 1, 4), searchspace=sp,
+                                                          direction="max", es_policy="none", name="asha_k9", seed=2))
+    d = holder["d"]
+    run = _run_dir()
+    trials = [json.load(open(os.path.join(run, t, "trial.json"))) for t in os.listdir(run)
+              if os.path.exists(os.path.join(run, t, "trial.json"))]
+    budgets = sorted(t["params"]["budget"] for t in trials)
+    assert budgets[0] == 1 and budgets[-1] == 4 and budgets.count(2) >= 2 and res["num_trials"] == len(trials)
+    assert d.device_decisions >= len(trials) - 2 and d.device_decision_fallbacks <= 1
+    assert d.device_handoffs >= 2                     # "fresh" decisions were handed over by the stand-in
+    handed = [t for t in trials if t["params"]["budget"] == 1]
+    assert len(handed) >= d.device_handoffs
+    # every promoted configuration carries its parent's hyperparameters and doubled budget
+    by_lr = {}
+    for t in trials:
+        by_lr.setdefault(round(t["params"]["lr"], 12), []).append(t["params"]["budget"])
+    assert any(sorted(b)[:2] == [1, 2] for b in by_lr.values())
+    lib.mgr_asha_free(state["tab"])
