@@ -277,9 +277,14 @@ class HyperparameterOptDriver(Driver):
                 return
             trial = self.controller.fresh_trial()
         payload = {"params": trial.params, "trial_type": trial.trial_type}
-        if self.channel.stage(worker, trial.trial_id, payload, self.controller.rung_of(trial) + 1):
-            trial._device_tagged = True
-            self._staged[worker] = trial
+        for _ in range(40):
+            # refused while the worker is still copying a hand-off out of the staged area (microseconds)
+            if self.channel.stage(worker, trial.trial_id, payload, self.controller.rung_of(trial) + 1):
+                trial._device_tagged = True
+                self._staged[worker] = trial
+                return
+            time.sleep(0.0001)
+        self._parked_orphans = getattr(self, "_parked_orphans", 0) + 1   # sampled but never parked: rung 0 ignores it
 
     def _suggest(self, finished_trial=None, worker=None):
         """Next Trial | "IDLE" | None. Uses the lookahead buffer when it holds something."""

@@ -537,8 +537,11 @@ int mgr_stage(void* hv, uint32_t w, uint64_t trial_id, const void* data, uint32_
   MgHeader* hd = h->hdr();
   if (w >= hd->num_workers || len > hd->payload_bytes) return -1;
   MgWorkerCtl* c = h->ctl(w);
-  const uint32_t next = load_acq(&c->assign_seq) + 1;
+  const uint32_t seq = load_acq(&c->assign_seq), next = seq + 1;
   if (load_acq(&c->staged_seq) == next) return -2;
+  // the CURRENT assignment may itself sit in the staged area (it was published from there): the worker must have copied
+  // it out (ack) before the area is overwritten
+  if (c->assign_src == 1 && load_acq(&c->ack_seq) != seq) return -2;
   if (len) std::memcpy(h->staged_buf(w), data, len);
   c->staged_len = len;
   c->staged_tag = tag;

@@ -25,6 +25,8 @@ void mgr_heartbeat(void*, uint32_t);
 int mgr_wait_assign(void*, uint32_t, int64_t, uint64_t*, void*, uint32_t, uint32_t*);
 int mgr_check_stop(void*, uint32_t, uint64_t);
 int mgr_assign(void*, uint32_t, uint64_t, const void*, uint32_t);
+int mgr_stage(void*, uint32_t, uint64_t, const void*, uint32_t, uint32_t);
+int mgr_publish_staged(void*, uint32_t);
 void mgr_stop_trial(void*, uint32_t, uint64_t);
 int mgr_read_blob(void*, uint32_t, void*, uint32_t);
 void mgr_start_pump(void*);
@@ -56,9 +58,23 @@ int main(int argc, char** argv) {
       }
       const char blob[] = "final-result";
       if (mgr_post_blob(h, w, MG_REC_FINAL, tid, N, 1.0, blob, sizeof blob, 5'000'000) != 0) errors++;
+      // second trial: parked by the driver thread, published by the "scheduler" thread (what K9 does from the GPU)
+      if (mgr_wait_assign(h, w, 5000000, &tid, buf, sizeof buf, &len) != 1 || tid != 0xB000u + w ||
+          std::strcmp(buf, "staged-params") != 0)
+        errors++;
+      for (int i = 0; i < 64; ++i)
+        while (mgr_post(h, w, MG_REC_METRIC, tid, i, 0.25 * i, 0) != 0) usleep(10);
+      if (mgr_post_blob(h, w, MG_REC_FINAL, tid, 64, 2.0, blob, sizeof blob, 5'000'000) != 0) errors++;
       mgr_close(h, 0);
     });
   }
+  std::atomic<bool> sched_run{true};
+  std::thread scheduler([&] {   // publishes whatever is parked, as soon as the worker has picked up its previous trial
+    while (sched_run.load()) {
+      for (int w = 0; w < W; ++w) (void)mgr_publish_staged(drv, w);
+      usleep(20);
+    }
+  });
   std::vector<int64_t> next_step(W, 0);
   std::vector<int> finals(W, 0);
   int regs = 0, done = 0;
@@ -75,21 +91,33 @@ int main(int argc, char** argv) {
         ++regs;
         const char payload[] = "params";
         while (mgr_assign(drv, w, 0xA000u + w, payload, sizeof payload) == -2) usleep(10);
+        const char staged[] = "staged-params";
+        while (mgr_stage(drv, w, 0xB000u + w, staged, sizeof staged, 1) == -2) usleep(10);
       } else if (r.type == MG_REC_METRIC) {
-        if (r.step != next_step[w] || r.value != 0.5 * r.step) errors++;
-        next_step[w] = r.step + 1;
-        if (r.step == N / 2) mgr_stop_trial(drv, w, 0xA000u + w);
+        if (r.trial_id == 0xA000u + w) {
+          if (r.step != next_step[w] || r.value != 0.5 * r.step) errors++;
+          next_step[w] = r.step + 1;
+          if (r.step == N / 2) mgr_stop_trial(drv, w, 0xA000u + w);
+        }
       } else if (r.type == MG_REC_FINAL) {
         int k = mgr_read_blob(drv, w, blob, sizeof blob);
         if (k <= 0 || std::strcmp(blob, "final-result") != 0) errors++;
         finals[w]++;
-        ++done;
+        if (finals[w] == 2) ++done;
+        // a third trial gets parked while the second one may still be copied out of the staged area: mgr_stage has to
+        // refuse until the worker acknowledged it (-2), never overwrite under the reader
+        if (finals[w] == 1) {
+          const char late[] = "never-run";
+          for (int tries = 0; tries < 200 && mgr_stage(drv, w, 0xC000u + w, late, sizeof late, 1) == -2; ++tries) usleep(10);
+        }
       }
     }
   }
   for (auto& t : workers) t.join();
+  sched_run.store(false);
+  scheduler.join();
   for (int w = 0; w < W; ++w)
-    if (next_step[w] != N || finals[w] != 1) errors++;
+    if (next_step[w] != N || finals[w] != 2) errors++;
   mgr_close(drv, 1);
   if (regs != W) errors++;
   printf("RING_STRESS %s errors=%d\n", errors.load() == 0 ? "OK" : "FAILED", errors.load());
