@@ -126,6 +126,26 @@ class BaseEnv:
         except OSError:
             return "127.0.0.1"
 
+    def connect_host(self, server_sock, server_host_port, exp_driver):
+        """Bind + listen a driver-side socket (reference: environment/base.py:137-150, the TCP RPC server's listener).
+        The control plane here is a shared-memory segment, so the only socket a driver opens is the optional external
+        LOG endpoint (core/logserver.py), which binds through this hook."""
+        if not server_host_port:
+            server_sock.bind(("", 0))
+            server_host_port = (self.get_ip_address(), server_sock.getsockname()[1])
+        else:
+            server_sock.bind(server_host_port)
+        server_sock.listen(10)
+        return server_sock, server_host_port
+
+    def get_client(self, server_addr, partition_id, hb_interval, secret, sock):
+        """The worker-side end of the control channel (reference: environment/base.py:217-222 builds the TCP ``Client``).
+        ``server_addr`` is the control segment's name here; heartbeat interval and secret have no role on a 0600
+        shared-memory segment handed to the worker by name (core/rpc.py module docstring)."""
+        from ..rpc import WorkerChannel
+
+        return WorkerChannel(server_addr, partition_id)
+
     def get_executors(self, default=None):
         from ... import util
 

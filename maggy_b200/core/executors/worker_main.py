@@ -32,6 +32,8 @@ def main(argv=None) -> int:
         if p not in sys.path:
             sys.path.append(p)
     os.environ["ML_ID"] = f"{spec['app_id']}_{spec['run_id']}"
+    os.environ["MAGGY_WORKER_ID"] = str(args.worker_id)       # util.get_partition_attempt_id()
+    os.environ["MAGGY_TASK_ATTEMPT"] = str(args.attempt)
 
     from ..environment.singleton import EnvSing
     from .. import rpc

@@ -420,3 +420,18 @@ class WorkerChannel:
                 self._dev = None
             self.lib.mgr_close(self.h, 0)
             self.h = None
+
+
+# ------------------------------------------------------------------------------------------------
+# names of the reference's maggy/core/rpc.py. The TCP server / client pair does not exist
+# here — one shared-memory segment replaces the sockets — so the reference's class names resolve to the object that plays
+# the same role on this control plane.
+# ------------------------------------------------------------------------------------------------
+from .reservations import MirroredReservations, Reservations  # noqa: E402,F401  (rpc.py:45-202 in the reference)
+
+Server = DriverChannel                     # rpc.py:260-392: listener + dispatch -> DriverChannel.next() / message callbacks
+OptimizationServer = DriverChannel         # rpc.py:395-511: REG / QUERY / METRIC / FINAL / GET / LOG
+DistributedTrainingServer = DriverChannel  # rpc.py:514-590: + EXEC_CONFIG (travels in the assign payload of gang trials)
+TensorflowServer = DriverChannel           # rpc.py:593-633: + TF_CONFIG / RESERVATIONS (MirroredReservations.get_spec)
+Client = WorkerChannel                     # rpc.py:636-802: heartbeat + GET polling -> records + futex-waited assign slot
+MessageSocket = MgRecord                   # rpc.py:205-257: the wire format is the 64-byte record (+ blob areas)

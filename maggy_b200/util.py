@@ -207,5 +207,26 @@ def finalize_experiment(experiment_json, metric, app_id, run_id, state, duration
                                                logdir, best_logdir, optimization_key)
 
 
+def get_partition_attempt_id():
+    """``(partition_id, attempt)`` of the calling worker process (reference: maggy/util.py:63-76 reads Spark's
+    TaskContext). Here the native launcher passes both on the worker's command line; ``worker_main`` exports them as
+    ``MAGGY_WORKER_ID`` / ``MAGGY_TASK_ATTEMPT``. In the driver process (no task context) this is ``(0, 0)``, like the
+    reference without Spark."""
+    return int(os.environ.get("MAGGY_WORKER_ID", "0")), int(os.environ.get("MAGGY_TASK_ATTEMPT", "0"))
+
+
+def find_spark():
+    """The SparkSession of the reference (maggy/util.py:246-253); this runtime never has one: workers are processes of
+    the native per-GPU pool (core/workerpool.py), so the answer is always None, like the reference without Spark."""
+    return None
+
+
+def set_app_id(app_id):
+    """Set the application id once (reference: maggy/util.py:339-347, used when the kernel is plain python)."""
+    global APP_ID
+    if APP_ID is None:
+        APP_ID = app_id
+
+
 def new_app_id() -> str:
     return f"application_{int(time.time() * 1000)}_0001"

@@ -189,3 +189,38 @@ def test_log_endpoint_serves_a_running_experiment(tmp_path, monkeypatch):
     EnvSing.reset()
     assert res["num_trials"] == 6
     assert seen.get("reply", {}).get("type") == "OK" and seen["reply"]["num_trials"] == 6
+
+
+def test_reference_util_and_environment_hooks_exist(monkeypatch):
+    """Names of the reference's util / BaseEnv surface that only make sense with Spark or TCP still answer
+    (maggy/util.py:63-76,246-253,339-347; environment/base.py:137-150,217-222)."""
+    import socket
+
+    from maggy_b200 import util
+    from maggy_b200.core import rpc
+    from maggy_b200.core.environment.base import BaseEnv
+
+    monkeypatch.delenv("MAGGY_WORKER_ID", raising=False)
+    assert util.get_partition_attempt_id() == (0, 0) and util.find_spark() is None
+    monkeypatch.setenv("MAGGY_WORKER_ID", "3")
+    monkeypatch.setenv("MAGGY_TASK_ATTEMPT", "2")
+    assert util.get_partition_attempt_id() == (3, 2)
+    old = util.APP_ID
+    util.APP_ID = None
+    util.set_app_id("application_1_0001")
+    util.set_app_id("application_2_0001")
+    assert util.APP_ID == "application_1_0001"
+    util.APP_ID = old
+    env = BaseEnv()
+    s = socket.socket()
+    s, (host, port) = env.connect_host(s, None, None)
+    assert port > 0 and host
+    s.close()
+    ch = rpc.DriverChannel(1, ring_slots=64, payload_bytes=1 << 16)
+    try:
+        w = env.get_client(ch.name, 0, 1, "secret", None)
+        w.register()
+        assert any(m["type"] == "REG" for m in ch.next(0.5))
+        w.close()
+    finally:
+        ch.close()
