@@ -131,8 +131,7 @@ class Driver(ABC):
         self.job_start = job_start
         self._register_msg_callbacks()
         self.channel = rpc.DriverChannel(self.num_executors, ring_slots=1024, payload_bytes=4 << 20)
-        self._digest_thread = threading.Thread(target=self._digest_loop, name="maggy-digest", daemon=True)
-        self._digest_thread.start()
+        self._start_worker()
         self._start_log_server()
 
     def _start_log_server(self) -> None:
@@ -232,6 +231,27 @@ class Driver(ABC):
             self._gstop_sent = True
 
     # ------------------------------------------------------------------ digest thread
+    def add_message(self, msg: dict) -> None:
+        """Hand one message to its callback (reference: spark_driver.py add_message puts it on the queue the digest
+        thread drains; here records arrive through the control segment, this entry serves injected messages — tests,
+        the external LOG endpoint)."""
+        cb = self.message_callbacks.get(msg["type"])
+        if cb is not None:
+            cb(msg)
+
+    @staticmethod
+    def _generate_secret(nbytes: int = 8) -> str:
+        """Random hex token (reference: spark_driver.py:70-73 authenticates TCP clients with it). The control segment's
+        name carries such a token and the segment is created 0600: knowing the name IS the credential."""
+        import secrets
+
+        return secrets.token_hex(nbytes)
+
+    def _start_worker(self) -> None:
+        """Start the digest thread (reference: spark_driver.py:211-217)."""
+        self._digest_thread = threading.Thread(target=self._digest_loop, name="maggy-digest", daemon=True)
+        self._digest_thread.start()
+
     def _digest_loop(self):
         try:
             while not self.worker_done:
@@ -239,9 +259,7 @@ class Driver(ABC):
                 if ch is None:
                     break
                 for msg in ch.next(timeout_s=0.02):
-                    cb = self.message_callbacks.get(msg["type"])
-                    if cb is not None:
-                        cb(msg)
+                    self.add_message(msg)
                 self._on_tick()
         except Exception as exc:  # noqa: BLE001
             self.log(traceback.format_exc())

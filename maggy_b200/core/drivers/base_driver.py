@@ -25,6 +25,7 @@ class BaseDriver(Driver):
         self.num_executors = 1
         self.results = []
         self.result_dict = {}
+        self.main_metric_key = None
 
     def _exp_startup_callback(self) -> None:
         pass
@@ -42,21 +43,68 @@ class BaseDriver(Driver):
         self.results.append(retval)
         self.experiment_done = True
 
-    def _exp_final_callback(self, job_end: float, exp_json: dict) -> dict:
+    # ---- the reference's BaseDriver surface (base_driver.py:59-142, 210-254), on top of the in-process run -----------
+    def _update_result(self, final_metric) -> None:
+        """Fold one run's return value into ``result_dict`` ({key: [values]}); the first key is the main metric."""
+        if isinstance(final_metric, dict):
+            if self.main_metric_key is None and final_metric:
+                self.main_metric_key = next(iter(final_metric))
+            for key, value in final_metric.items():
+                self.result_dict.setdefault(key, []).append(value)
+
+    def _final_msg_callback(self, msg: dict) -> None:
+        final_metric = msg.get("data", None)
+        self.results.append(final_metric)
+        self._update_result(final_metric)
+
+    def _log_msg_callback(self, msg: dict) -> None:
+        if msg.get("data"):
+            self.add_executor_logs(msg["data"] if isinstance(msg["data"], str) else str(msg["data"]))
+
+    def average_metrics(self) -> float:
+        """Mean of the numeric results so far (0 if there is none yet)."""
+        vals = [r for r in self.results if isinstance(r, (int, float)) and not isinstance(r, bool)]
+        return sum(vals) / len(vals) if vals else 0
+
+    def prep_results(self, duration_str: str) -> str:
+        return f"Results ------\nMetrics value {self.result}\nTotal job time {duration_str}\n"
+
+    def json(self) -> str:
+        exp = {"project": EnvSing.get_instance().project_name(), "user": os.environ.get("HADOOP_USER_NAME"),
+               "name": self.name, "module": "maggy", "app_id": str(self.app_id),
+               "start": __import__("time").strftime("%Y-%m-%dT%H:%M:%S", __import__("time").localtime(self.job_start)),
+               "executors": self.num_executors, "logdir": self.log_dir, "description": self.description,
+               "experiment_type": "base"}
+        if self.experiment_done:
+            exp.update({"status": "FINISHED", "duration": self.duration,
+                        "finished": __import__("time").strftime("%Y-%m-%dT%H:%M:%S",
+                                                                __import__("time").localtime(self.job_end))})
+            if self.main_metric_key is not None and self.result_dict.get(self.main_metric_key):
+                exp["metric"] = self.result_dict[self.main_metric_key][-1]
+        else:
+            exp["status"] = "RUNNING"
+        return json.dumps(exp, default=util.json_default_numpy)
+
+    def finalize(self, job_end: float) -> dict:
+        """Summarise the run: ``result.json`` + ``maggy.json`` in the log directory, the summary line in ``maggy.log``."""
         self.job_end = job_end
         self.duration = util.seconds_to_milliseconds(job_end - self.job_start)
-        result = self.average_metric()
-        self.result = {"test result": result}
+        for r in self.results:
+            self._update_result(r)
+        self.result = {"test result": self.average_metric()}
+        summary = self.prep_results(util.time_diff(self.job_start, job_end))
+        self.log(summary)
         env = EnvSing.get_instance()
         env.dump(json.dumps(self.result, default=util.json_default_numpy), os.path.join(self.log_dir, "result.json"))
-        env.dump(json.dumps({"name": self.name, "module": "maggy", "app_id": str(self.app_id), "logdir": self.log_dir,
-                             "description": self.description, "experiment_type": "base", "status": "FINISHED",
-                             "duration": self.duration}, default=util.json_default_numpy),
-                 os.path.join(self.log_dir, "maggy.json"))
+        env.dump(self.json(), os.path.join(self.log_dir, "maggy.json"))
+        return self.result
+
+    def _exp_final_callback(self, job_end: float, exp_json: dict) -> dict:
+        result = self.finalize(job_end)
         util.finalize_experiment(exp_json, None, self.app_id, self.run_id, "FINISHED", self.duration, self.log_dir,
                                  None, None)
         print(f"List of the results:\n{self.result}" if self.results else "No results")
-        return self.result
+        return result
 
     def average_metric(self):
         """dict results -> {key: [values over runs]}; numbers -> their mean; anything else as is."""

@@ -130,7 +130,7 @@ class HyperparameterOptDriver(Driver):
         self.message_callbacks.update({
             "REG": self._register_msg_callback, "METRIC": self._metric_msg_callback,
             "FINAL": self._final_msg_callback, "LOG": self._log_msg_callback,
-            "ERROR": self._error_msg_callback, "IDLE": lambda msg: None, "EXIT": lambda msg: None,
+            "ERROR": self._error_msg_callback, "IDLE": self._idle_msg_callback, "EXIT": lambda msg: None,
         })
 
     def init(self, job_start: float) -> None:
@@ -456,20 +456,32 @@ class HyperparameterOptDriver(Driver):
     # ------------------------------------------------------------------ message callbacks
     def _register_msg_callback(self, msg) -> None:
         worker = msg["partition_id"]
-        lost = self._assigned.get(worker)
-        if lost is not None:
-            # a restarted worker re-registers while a trial is still assigned to it: the reference marks the
-            # trial ERROR and re-schedules the very same trial on this partition (BLACK, rpc.py:421-432)
-            trial = self.get_trial(lost)
-            if trial is not None:
-                trial.status = Trial.ERROR
-                self.log(f"worker {worker} re-registered (attempt {msg['aux']}): rescheduling lost trial {lost}")
-                trial.metric_history, trial.step_history, trial.metric_dict = [], [], {}
-                trial.early_stop = False
-                self._scheduled -= 1
-                self._schedule(worker, trial)
-                return
+        if self._assigned.get(worker) is not None and self._blacklist_msg_callback(msg):
+            return
         self._assign_next(worker, None)
+
+    def _blacklist_msg_callback(self, msg) -> bool:
+        """A restarted worker re-registered while a trial is still assigned to it: the reference marks the trial ERROR
+        and re-schedules the very same trial on this partition (BLACK message, rpc.py:421-432,
+        optimization_driver.py:473-483). Returns True when a lost trial was rescheduled."""
+        worker = msg["partition_id"]
+        lost = self._assigned.get(worker)
+        trial = self.get_trial(lost) if lost is not None else None
+        if trial is None:
+            return False
+        trial.status = Trial.ERROR
+        self.log(f"worker {worker} re-registered (attempt {msg.get('aux')}): rescheduling lost trial {lost}")
+        trial.metric_history, trial.step_history, trial.metric_dict = [], [], {}
+        trial.early_stop = False
+        self._scheduled -= 1
+        self._schedule(worker, trial)
+        return True
+
+    def _idle_msg_callback(self, msg) -> None:
+        """A worker without work asks again (reference: optimization_driver.py:540-553 retries every 0.1 s)."""
+        worker = msg["partition_id"]
+        if worker in self._idle and not self.experiment_done:
+            self._assign_next(worker, self._idle[worker][1])
 
     def _metric_msg_callback(self, msg) -> None:
         trial = self.get_trial(msg["trial_id"])
