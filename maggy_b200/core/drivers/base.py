@@ -97,6 +97,19 @@ class Driver(ABC):
     def _picklable_config(self, config):
         return config
 
+    def _patching_fn(self, train_fn: Callable, config, is_spark_available: bool = False) -> Callable:
+        """``executor_fn(partition_id)`` for this driver's executor kind (reference: every driver's ``_patching_fn``
+        returns the closure Spark runs on its executors). The native pool normally starts the same loop through
+        ``worker_main``; calling the returned function runs it in the current process against this driver's segment."""
+        from ..executors.worker_main import run_executor
+
+        spec, segment = self._worker_spec(train_fn, config), self.channel.name
+
+        def executor_fn(partition_id, attempt: int = 0):
+            return run_executor(spec, segment, int(partition_id), attempt)
+
+        return executor_fn
+
     def _on_tick(self) -> None:
         """Called every digest iteration (idle retries, timers)."""
 

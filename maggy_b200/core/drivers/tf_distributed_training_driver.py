@@ -99,18 +99,42 @@ class TfDistributedTrainingDriver(Driver):
         vals = [v for v in self.results if isinstance(v, (int, float))]
         return sum(vals) / len(vals) if vals else None
 
-    def _exp_final_callback(self, job_end: float, exp_json: dict) -> dict:
+    # ---- the reference driver's result surface (tf_distributed_training_driver.py:60-142, 262-271) ------------------
+    def set_result(self, result) -> None:
+        self.results.append(result)
+
+    def set_final_model(self, final_model) -> None:
+        self.final_model = final_model
+
+    def _update_result(self, final_metric) -> None:
+        self.set_result(final_metric)
+
+    def prep_results(self, duration_str: str) -> str:
+        return f"Results ------\nAverage metric over {self.num_executors} workers {self.average_metric()}\n" \
+               f"Total job time {duration_str}\n"
+
+    def json(self) -> str:
+        exp = {"name": self.name, "module": "maggy", "app_id": str(self.app_id), "logdir": self.log_dir,
+               "executors": self.num_executors, "description": self.description, "experiment_type": "tf_dist",
+               "cluster": self.cluster_spec}
+        if self.experiment_done:
+            exp.update({"status": "FINISHED", "duration": self.duration, "metric": self.average_metric()})
+        else:
+            exp["status"] = "RUNNING"
+        return json.dumps(exp, default=util.json_default_numpy)
+
+    def finalize(self, job_end: float) -> dict:
         self.job_end = job_end
         self.duration = util.seconds_to_milliseconds(job_end - self.job_start)
-        result = self.average_metric()
-        self.result = {"test result": result}
+        self.result = {"test result": self.average_metric()}
+        self.log(self.prep_results(util.time_diff(self.job_start, job_end)))
         env = EnvSing.get_instance()
         env.dump(json.dumps(self.result, default=util.json_default_numpy), os.path.join(self.log_dir, "result.json"))
-        env.dump(json.dumps({"name": self.name, "module": "maggy", "app_id": str(self.app_id), "logdir": self.log_dir,
-                             "executors": self.num_executors, "description": self.description,
-                             "experiment_type": "tf_dist", "cluster": self.cluster_spec, "status": "FINISHED",
-                             "duration": self.duration, "metric": result}, default=util.json_default_numpy),
-                 os.path.join(self.log_dir, "maggy.json"))
+        env.dump(self.json(), os.path.join(self.log_dir, "maggy.json"))
+        return self.result
+
+    def _exp_final_callback(self, job_end: float, exp_json: dict) -> dict:
+        result = self.finalize(job_end)["test result"]
         util.finalize_experiment(exp_json, result, self.app_id, self.run_id, "FINISHED", self.duration, self.log_dir,
                                  None, None)
         print(f"Final average test loss: {result}" if result is not None else "No metric returned")

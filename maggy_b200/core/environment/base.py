@@ -126,6 +126,9 @@ class BaseEnv:
         except OSError:
             return "127.0.0.1"
 
+    def _upload_file_output(self, retval, hdfs_exec_logdir):
+        """Hook for environments with a remote file system (reference: environment/base.py:152-153); local: nothing."""
+
     def connect_host(self, server_sock, server_host_port, exp_driver):
         """Bind + listen a driver-side socket (reference: environment/base.py:137-150, the TCP RPC server's listener).
         The control plane here is a shared-memory segment, so the only socket a driver opens is the optional external

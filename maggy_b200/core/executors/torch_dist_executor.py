@@ -133,3 +133,13 @@ def torch_dist_executor_loop(spec, channel, worker_id, attempt):
         except Exception:
             pass
         reporter.close_logger()
+
+
+
+def torch_dist_executor_fn(train_fn, config, experiment_type, app_id, run_id, server_addr, hb_interval, secret, optimization_key, log_dir):
+    """The reference's executor factory (same argument list): ``executor_fn(partition_id)`` that attaches to the control
+    segment ``server_addr`` and runs this module's loop — see ``worker_main.make_executor_fn``."""
+    from .worker_main import make_executor_fn
+
+    return make_executor_fn("torch_dist", train_fn, config, experiment_type, app_id, run_id, server_addr, hb_interval, secret,
+                            optimization_key, log_dir)

@@ -198,3 +198,13 @@ def _follower_loop(spec, worker_id, attempt, gang, log_dir):
         reporter.set_trial_id(trial_id)
         run_one_trial(spec, trial_id, payload["params"], reporter, log_dir, gang)
         reporter.reset()
+
+
+
+def trial_executor_fn(train_fn, config, experiment_type, app_id, run_id, server_addr, hb_interval, secret, optimization_key, log_dir):
+    """The reference's executor factory (same argument list): ``executor_fn(partition_id)`` that attaches to the control
+    segment ``server_addr`` and runs this module's loop — see ``worker_main.make_executor_fn``."""
+    from .worker_main import make_executor_fn
+
+    return make_executor_fn("trial", train_fn, config, experiment_type, app_id, run_id, server_addr, hb_interval, secret,
+                            optimization_key, log_dir)

@@ -26,6 +26,11 @@ def _to_device(obj, device, non_blocking=True):
     return obj
 
 
+def _to_cuda(data):
+    """Recursively move a batch to the current CUDA device (reference: patching/dataloader.py:147-163)."""
+    return _to_device(data, torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cpu")
+
+
 class MaggyDataLoader(DataLoader):
     def __init__(self, dataset, batch_size=1, shuffle=False, sampler=None, **kwargs):
         self._device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None

@@ -32,13 +32,25 @@ def _find_fused_owner(params):
     return flat, params
 
 
+class MaggyZeroOptimizer:
+    """Marker base of every ``MaggyZero<Name>`` class (reference: patching/optim.py:28-45 subclasses torch's
+    ZeroRedundancyOptimizer; here construction dispatches to the fused arena optimizer, ZeRO-1 or the plain optimizer,
+    see :func:`make_zero_optimizer`). ``optim_cls`` is bound by the generated subclasses."""
+
+    optim_cls = None
+
+
 def make_zero_optimizer(optim_cls, zero_lvl: int = 1):
     """``MaggyZero<Name>``: same constructor as ``optim_cls``. Parameters that live in a fused ``DataParallel`` arena
     get the fused (and sharded) path at every ZeRO level — there is no DDP underneath that would reduce their
     gradients otherwise; other parameters get ``ZeroRedundancyOptimizer`` for ``zero_lvl`` 1-2 like the reference and
     the plain optimizer for level 0."""
 
-    class MaggyZeroOptimizer:
+    _bound = optim_cls
+
+    class _MaggyZero(MaggyZeroOptimizer):
+        optim_cls = _bound
+
         def __new__(cls, params, *args, **kwargs):
             flat, params = _find_fused_owner(params)
             # (by name: inside patched_optimizers() torch.optim.Adam IS the patched class, not the saved original)
@@ -79,8 +91,8 @@ def make_zero_optimizer(optim_cls, zero_lvl: int = 1):
                 return ZeroRedundancyOptimizer(params, optimizer_class=optim_cls, **kw)
             return optim_cls(params, *args, **kwargs)
 
-    MaggyZeroOptimizer.__name__ = f"MaggyZero{optim_cls.__name__}"
-    return MaggyZeroOptimizer
+    _MaggyZero.__name__ = _MaggyZero.__qualname__ = f"MaggyZero{optim_cls.__name__}"
+    return _MaggyZero
 
 
 MaggyZeroAdadelta, MaggyZeroAdagrad, MaggyZeroAdam, MaggyZeroAdamW, MaggyZeroSparseAdam, MaggyZeroAdamax, \

@@ -260,3 +260,48 @@ def test_prefetched_trial_is_parked_then_published():
         w.close()
     finally:
         ch.close()
+
+
+def test_executor_factory_runs_the_trial_loop_in_process(tmp_path, monkeypatch):
+    """trial_executor_fn(...) (the reference's factory signature) -> executor_fn(partition_id): attaches to the control
+    segment by name and serves trials; driven here by a bare DriverChannel (REG -> assign -> METRIC/FINAL -> GSTOP)."""
+    import threading
+
+    from maggy_b200.core import rpc
+    from maggy_b200.core.environment.singleton import EnvSing
+    from maggy_b200.core.executors.trial_executor import trial_executor_fn
+
+    monkeypatch.setenv("MAGGY_LOG_DIR", str(tmp_path / "experiment_log"))
+    EnvSing.reset()
+    log_dir = str(tmp_path / "run")
+    os.makedirs(log_dir, exist_ok=True)
+
+    def train_fn(hparams, reporter):
+        reporter.broadcast(hparams["x"] * 2.0, 0)
+        return hparams["x"] * 2.0
+
+    class Cfg:
+        name, description, hb_interval, optimization_key, model, dataset = "f", "", 1, "Metric", None, None
+
+    ch = rpc.DriverChannel(1, ring_slots=64, payload_bytes=1 << 16)
+    try:
+        fn = trial_executor_fn(train_fn, Cfg(), "optimization", "application_1_0001", 1, ch.name, 1, None, "Metric", log_dir)
+        rc = {}
+        t = threading.Thread(target=lambda: rc.setdefault("rc", fn(0)), daemon=True)
+        t.start()
+        seen, deadline = [], time.time() + 30
+        assigned = False
+        while time.time() < deadline and not any(m["type"] == "FINAL" for m in seen):
+            for m in ch.next(0.05):
+                seen.append(m)
+                if m["type"] == "REG" and not assigned:
+                    assert ch.assign(0, "00000000000000f1", {"params": {"x": 1.5}, "trial_type": "optimization"})
+                    assigned = True
+        finals = [m for m in seen if m["type"] == "FINAL"]
+        assert finals and finals[0]["trial_id"] == "00000000000000f1" and finals[0]["data"]["metric"] == 3.0
+        ch.gstop()
+        t.join(10)
+        assert not t.is_alive() and rc.get("rc") == 0
+    finally:
+        ch.close()
+        EnvSing.reset()
