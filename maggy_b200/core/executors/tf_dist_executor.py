@@ -141,3 +141,10 @@ def dist_executor_fn(train_fn, config, experiment_type, app_id, run_id, server_a
 
     return make_executor_fn("tf_dist", train_fn, config, experiment_type, app_id, run_id, server_addr, hb_interval, secret,
                             optimization_key, log_dir)
+
+
+
+def find_index(host_port, reservations):
+    """Index of ``host_port`` among the cluster's workers, -1 if absent (reference: tf_dist_executor.py:467-480)."""
+    workers = reservations["cluster"]["worker"]
+    return workers.index(host_port) if host_port in workers else -1

@@ -255,6 +255,27 @@ class DriverChannel:
     def stop_time_ns(self, worker: int) -> int:
         return int(self.lib.mgr_stop_time_ns(self.h, worker))
 
+    # -- the reference Server's method names (rpc.py:282-305, 335-392, 504-511) ---------------------------------------
+    def start(self, exp_driver=None):
+        """The segment exists and its pump runs from construction on; returns the "address" workers attach to
+        (reference: ``Server.start`` returns ``(host, port)``)."""
+        return self.name, self.num_workers
+
+    def stop(self):
+        self.close()
+
+    def await_reservations(self, sc=None, status=None, timeout=600):
+        """Block until every worker has registered (messages are drained by whoever calls :meth:`next`)."""
+        deadline = time.time() + timeout
+        while not self.reservations.done():
+            if time.time() > deadline:
+                raise TimeoutError(f"{self.reservations.remaining()} workers did not register within {timeout} s")
+            time.sleep(0.01)
+        return self.reservations.get()
+
+    def get_assigned_trial_id(self, partition_id: int):
+        return self.reservations.get_assigned_trial(partition_id)
+
     def close(self, unlink: bool = True):
         if self.h:
             self.lib.mgr_close(self.h, 1 if unlink else 0)
@@ -287,6 +308,8 @@ class WorkerChannel:
         # ablation trial): size the receive buffer from the header, not from a constant
         self._payload = ctypes.create_string_buffer(max(1 << 16, int(self.lib.mgr_payload_bytes(self.h))))
         self._dev = None  # lazily created device-side producer state
+        self._current_trial = None  # last trial handed out by get_suggestion()
+        self._hb = None
 
     def register(self):
         rc = self.lib.mgr_register(self.h, self.worker, self.attempt, os.getpid())
@@ -403,6 +426,54 @@ class WorkerChannel:
         if rc != 0:
             raise RuntimeError(f"mg_report_store failed: {rc}")
 
+    # -- the reference Client's method names (rpc.py:708-802) ------------------------------------------------------
+    def await_reservations(self):
+        """Nothing to wait for: rendezvous facts of gang / distributed runs travel in the assign payload."""
+        return True
+
+    def start_heartbeat(self, reporter, interval_s: float = 1.0):
+        """Sign-of-life thread (the reference's heartbeat also carried metrics; here they are ring records)."""
+        from .executors.trial_executor import _start_heartbeat
+
+        self._hb = _start_heartbeat(self, interval_s, reporter)
+        return self._hb
+
+    def get_suggestion(self, reporter=None, timeout_s: float = None):
+        """Block until the driver (or the device scheduler) hands over the next trial: ``(trial_id, params)``;
+        ``(None, None)`` once the experiment is over (reference: polls GET with ``sleep(1)``, rpc.py:739-748)."""
+        deadline = None if timeout_s is None else time.time() + timeout_s
+        while deadline is None or time.time() < deadline:
+            got = self.wait_assign(1.0)
+            if got is WorkerChannel.GSTOP:
+                return None, None
+            if got is not None:
+                trial_id, payload = got
+                self._current_trial = trial_id
+                return trial_id, (payload or {}).get("params", payload)
+        return None, None
+
+    def get_message(self, msg_type, timeout=60):
+        """The request / reply pairs of the TCP protocol that still have an answer on the shared segment."""
+        if msg_type == "GET":
+            return self.get_suggestion(timeout_s=timeout)
+        if msg_type == "QUERY":
+            return True   # reservations complete: the pool only assigns trials to registered workers
+        raise NotImplementedError(f"{msg_type}: no request/reply exchange on the shared-memory control plane")
+
+    def finalize_metric(self, metric, reporter=None):
+        """FINAL + reporter reset (reference: rpc.py:793-802 holds the reporter lock across both)."""
+        if reporter is None:
+            return self.post_final(self._current_trial, metric)
+        with reporter.lock:
+            _, _, logs = reporter.get_data()
+            self.post_final(reporter.trial_id or self._current_trial, metric, {"logs": logs} if logs else None)
+            reporter.reset()
+
+    def stop(self):
+        if self._hb is not None:
+            self._hb.set()   # the heartbeat thread's stop event
+        self.close()
+
     def close(self):
         if self.h:
             if self._dev is not None:
@@ -434,4 +505,25 @@ OptimizationServer = DriverChannel         # rpc.py:395-511: REG / QUERY / METRI
 DistributedTrainingServer = DriverChannel  # rpc.py:514-590: + EXEC_CONFIG (travels in the assign payload of gang trials)
 TensorflowServer = DriverChannel           # rpc.py:593-633: + TF_CONFIG / RESERVATIONS (MirroredReservations.get_spec)
 Client = WorkerChannel                     # rpc.py:636-802: heartbeat + GET polling -> records + futex-waited assign slot
-MessageSocket = MgRecord                   # rpc.py:205-257: the wire format is the 64-byte record (+ blob areas)
+
+
+class MessageSocket:
+    """rpc.py:205-257 framed cloudpickled dicts over TCP. The wire format here is the 64-byte :class:`MgRecord` plus the
+    per-worker blob areas; ``send`` / ``receive`` map onto a channel's post / next."""
+
+    Record = MgRecord
+
+    @staticmethod
+    def send(channel, msg: dict):
+        kind = msg.get("type")
+        if kind == "METRIC":
+            return channel.post_metric(msg["trial_id"], msg["data"]["value"], msg["data"].get("step", 0))
+        if kind == "FINAL":
+            return channel.post_final(msg["trial_id"], msg["data"])
+        if kind == "LOG":
+            return channel.post_log(msg.get("trial_id"), msg.get("data", ""))
+        raise NotImplementedError(f"message type {kind}")
+
+    @staticmethod
+    def receive(channel, timeout_s: float = 0.1):
+        return channel.next(timeout_s)

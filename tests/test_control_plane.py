@@ -305,3 +305,41 @@ def test_executor_factory_runs_the_trial_loop_in_process(tmp_path, monkeypatch):
     finally:
         ch.close()
         EnvSing.reset()
+
+
+def test_reference_server_and_client_method_names():
+    """DriverChannel / WorkerChannel answer to the reference's Server / Client vocabulary (start, await_reservations,
+    get_suggestion, finalize_metric, stop, MessageSocket.send / receive, get_assigned_trial_id)."""
+    from maggy_b200.core import rpc
+
+    server = rpc.OptimizationServer(1, ring_slots=64, payload_bytes=1 << 16)
+    try:
+        addr, n = server.start()
+        client = rpc.Client(addr, 0)
+        client.register()
+        assert any(m["type"] == "REG" for m in rpc.MessageSocket.receive(server, 0.5))
+        assert server.await_reservations(timeout=1)[0]["partition_id"] == 0 if "partition_id" in server.reservations.get()[0] \
+            else server.reservations.done()
+        assert client.await_reservations() and client.get_message("QUERY") is True
+        stop = client.start_heartbeat(None, interval_s=0.01)
+        assert server.assign(0, "00000000000000aa", {"params": {"lr": 0.5}})
+        trial_id, params = client.get_suggestion()
+        assert trial_id == "00000000000000aa" and params == {"lr": 0.5}
+        assert server.get_assigned_trial_id(0) == "00000000000000aa"
+        rpc.MessageSocket.send(client, {"type": "METRIC", "trial_id": trial_id, "data": {"value": 0.25, "step": 3}})
+        client.finalize_metric(0.75)
+        msgs = []
+        for _ in range(20):
+            msgs += server.next(0.05)
+            if any(m["type"] == "FINAL" for m in msgs):
+                break
+        assert any(m["type"] == "METRIC" and m["value"] == 0.25 and m["step"] == 3 for m in msgs)
+        assert any(m["type"] == "FINAL" and m["trial_id"] == trial_id and m["data"]["metric"] == 0.75 for m in msgs)
+        with pytest.raises(NotImplementedError):
+            client.get_message("TF_CONFIG")
+        server.gstop()
+        assert client.get_suggestion(timeout_s=2) == (None, None)
+        client.stop()
+        assert stop.is_set()
+    finally:
+        server.stop()
