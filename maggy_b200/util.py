@@ -44,15 +44,10 @@ def progress_bar(done: int, total: int) -> str:
 
 
 def time_diff(t0: float, t1: float) -> str:
-    """Human readable ``t1 - t0`` (seconds since epoch)."""
-    secs = int(max(0.0, t1 - t0))
-    h, rem = divmod(secs, 3600)
-    m, s = divmod(rem, 60)
-    if h:
-        return f"{h} hours, {m} minutes, {s} seconds"
-    if m:
-        return f"{m} minutes, {s} seconds"
-    return f"{s} seconds"
+    """Human readable ``t1 - t0`` (seconds since epoch), in the reference's fixed format (maggy/util.py:263-272)."""
+    minutes, seconds = divmod(max(0.0, t1 - t0), 60)
+    hours, minutes = divmod(minutes, 60)
+    return "%d hours, %d minutes, %d seconds" % (hours, minutes, seconds)
 
 
 def seconds_to_milliseconds(t: float) -> int:

@@ -1,0 +1,201 @@
+"""Differential tests against the UNMODIFIED reference package (baseline/_ref, imported under its own name next to the
+import-time stand-ins of baseline/refenv): same inputs -> same trial ids, encodings, schedules and stop decisions.
+Skipped when the reference is not installed (it is git-ignored)."""
+import importlib
+import json
+import os
+import random
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF_DIR, "maggy")), reason="reference not installed")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    """The reference's modules under the names ``ref.searchspace`` ... (the ``maggy`` alias of this repo is put back
+    afterwards)."""
+    sys.path.insert(0, ROOT)
+    from baseline import refenv
+
+    refenv.install()
+    saved = {k: v for k, v in sys.modules.items() if k == "maggy" or k.startswith("maggy.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, REF_DIR)
+    try:
+        import maggy  # noqa: F401
+
+        assert os.path.realpath(maggy.__file__).startswith(os.path.realpath(REF_DIR))
+
+        class R:
+            searchspace = importlib.import_module("maggy.searchspace")
+            trial = importlib.import_module("maggy.trial")
+            hyperband = importlib.import_module("maggy.pruner.hyperband")
+            median = importlib.import_module("maggy.earlystop.medianrule")
+            util = importlib.import_module("maggy.util")
+            asha = importlib.import_module("maggy.optimizer.asha")
+
+        yield R
+    finally:
+        sys.path.remove(REF_DIR)
+        for k in [k for k in sys.modules if k == "maggy" or k.startswith("maggy.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_trial_ids_and_json_match(ref):
+    from maggy_b200.trial import Trial
+
+    rng = random.Random(0)
+    for _ in range(50):
+        params = {"lr": rng.random(), "units": rng.randint(1, 512), "act": rng.choice(["relu", "gelu"]),
+                  "nested": [rng.random(), rng.randint(0, 9)]}
+        a, b = Trial(dict(params)), ref.trial.Trial(dict(params))
+        assert a.trial_id == b.trial_id and len(a.trial_id) == 16
+        for step, v in enumerate([0.1, 0.5, 0.4]):
+            assert a.append_metric({"value": v, "step": step}) == b.append_metric({"value": v, "step": step})
+        assert a.append_metric({"value": 0.9, "step": 2}) == b.append_metric({"value": 0.9, "step": 2})   # duplicate step
+        ja, jb = json.loads(a.to_json()), json.loads(b.to_json())
+        for key in ("trial_id", "params", "metric_history", "step_history", "status", "early_stop", "final_metric"):
+            assert ja[key] == jb[key], key
+    # ablation trials hash only the ablated component
+    p = {"ablated_feature": "age", "ablated_layer": "None", "dataset_function": len, "model_function": print}
+    assert Trial(p, trial_type="ablation").trial_id == ref.trial.Trial(p, trial_type="ablation").trial_id
+
+
+def test_searchspace_encoding_matches(ref):
+    from maggy_b200 import Searchspace
+
+    kw = dict(lr=("DOUBLE", [1e-4, 0.5]), units=("INTEGER", [8, 256]), drop=("DISCRETE", [0.1, 0.3, 0.5]),
+              act=("CATEGORICAL", ["relu", "gelu", "tanh"]))
+    a, b = Searchspace(**kw), ref.searchspace.Searchspace(**kw)
+    assert a.to_dict() == b.to_dict() and a.names() == b.names() and list(a.keys()) == list(b.keys())
+    assert [dict(i) for i in a] == [dict(i) for i in b]
+    rng = random.Random(1)
+    for _ in range(40):
+        h = {"lr": rng.uniform(1e-4, 0.5), "units": rng.randint(8, 256), "act": rng.choice(["relu", "gelu", "tanh"])}
+        sub_a = Searchspace(lr=kw["lr"], units=kw["units"], act=kw["act"])
+        sub_b = ref.searchspace.Searchspace(lr=kw["lr"], units=kw["units"], act=kw["act"])
+        assert sub_a.dict_to_list(h) == sub_b.dict_to_list(h)
+        for norm_cat in (False, True):
+            ta = sub_a.transform(sub_a.dict_to_list(h), normalize_categorical=norm_cat)
+            tb = sub_b.transform(sub_b.dict_to_list(h), normalize_categorical=norm_cat)
+            assert list(ta) == pytest.approx(list(tb))
+            ia = sub_a.inverse_transform(ta, normalize_categorical=norm_cat)
+            ib = sub_b.inverse_transform(tb, normalize_categorical=norm_cat)
+            assert list(ia)[2] == list(ib)[2] and list(ia)[:2] == pytest.approx(list(ib)[:2])
+        assert sub_a.list_to_dict(sub_a.dict_to_list(h)) == sub_b.list_to_dict(sub_b.dict_to_list(h))
+    for bad in (dict(x=("DOUBLE", [1.0])), dict(x=("INTEGER", [1.5, 3])), dict(x=("FOO", [1, 2]))):
+        with pytest.raises(Exception) as ea:
+            Searchspace(**bad)
+        with pytest.raises(Exception) as eb:
+            ref.searchspace.Searchspace(**bad)
+        assert type(ea.value) is type(eb.value)
+
+
+@pytest.mark.parametrize("cfg", [(1, 9, 3, 3), (1, 27, 3, 4), (2, 32, 2, 5), (1, 81, 3, 2)])
+def test_hyperband_schedules_match(ref, cfg):
+    from maggy_b200.pruner.hyperband import Hyperband
+
+    mn, mx, eta, n_it = cfg
+    getter = lambda trial_ids=None: {}  # noqa: E731
+    a = Hyperband(min_budget=mn, max_budget=mx, eta=eta, n_iterations=n_it, trial_metric_getter=getter)
+    b = ref.hyperband.Hyperband(min_budget=mn, max_budget=mx, eta=eta, n_iterations=n_it, trial_metric_getter=getter)
+    assert list(a.budgets) == pytest.approx(list(b.budgets)) and a.max_sh_rungs == b.max_sh_rungs
+    assert a.num_trials() == b.num_trials()
+    assert [list(it.n_configs) for it in a.iterations] == [list(it.n_configs) for it in b.iterations]
+    assert [list(it.budgets) for it in a.iterations] == [pytest.approx(list(it.budgets)) for it in b.iterations]
+
+
+def test_median_rule_decisions_match(ref):
+    from maggy_b200.earlystop import MedianStoppingRule
+    from maggy_b200.trial import Trial
+
+    rng = random.Random(3)
+    for direction in ("max", "min"):
+        finals_a, finals_b = [], []
+        for i in range(8):
+            hist = [rng.random() for _ in range(rng.randint(3, 12))]
+            for store, cls in ((finals_a, Trial), (finals_b, ref.trial.Trial)):
+                t = cls({"i": i})
+                for s, v in enumerate(hist):
+                    t.append_metric({"value": v, "step": s})
+                t.status = cls.FINALIZED
+                store.append(t)
+        for _ in range(60):
+            hist = [rng.random() for _ in range(rng.randint(1, 12))]
+            ta, tb = Trial({"r": rng.random()}), ref.trial.Trial({"r": 0})
+            for s, v in enumerate(hist):
+                ta.append_metric({"value": v, "step": s})
+                tb.append_metric({"value": v, "step": s})
+            da = MedianStoppingRule.earlystop_check(ta, finals_a, direction)
+            try:
+                db = ref.median.MedianStoppingRule.earlystop_check(tb, finals_b, direction)
+            except Exception:   # the reference raises when no finalized trial is that long (its driver logs and moves on)
+                db = None
+            assert (da is None) == (db is None), (direction, hist)
+
+
+def test_util_formatting_matches(ref):
+    from maggy_b200 import util
+
+    for done, total in ((0, 10), (3, 10), (10, 10), (7, 7), (1, 3)):
+        assert util.progress_bar(done, total) == ref.util.progress_bar(done, total)
+    for t0, t1 in ((0.0, 5.0), (10.0, 75.5), (0.0, 3725.0), (100.0, 100.4)):
+        assert util.time_diff(t0, t1) == ref.util.time_diff(t0, t1)
+    assert util.seconds_to_milliseconds(1.2345) == ref.util.seconds_to_milliseconds(1.2345)
+
+
+@pytest.mark.parametrize("rf,rmin,rmax", [(2, 1, 4), (3, 1, 27), (2, 1, 16), (4, 2, 32)])
+def test_asha_decision_stream_matches_for_maximisation(ref, rf, rmin, rmax):
+    """Same finished-trial stream into both optimizers (configurations drawn from a shared counter instead of each
+    one's RNG): identical sequence of (fresh | promoted, budget, parent configuration) and the same closing point.
+    direction="max": the reference ranks descending whatever the direction (asha.py:161-169), this one honours it."""
+    from maggy_b200.optimizer import Asha
+    from maggy_b200.trial import Trial
+
+    class CounterSpace:
+        def __init__(self):
+            self.n = 0
+
+        def get_random_parameter_values(self, k):
+            out = []
+            for _ in range(k):
+                self.n += 1
+                out.append({"x": float(self.n)})
+            return out
+
+    def build(cls, trial_cls):
+        opt = cls(reduction_factor=rf, resource_min=rmin, resource_max=rmax)
+        opt.searchspace, opt.num_trials, opt.direction = CounterSpace(), 10 ** 6, "max"
+        opt.trial_store, opt.final_store = {}, []
+        opt.initialize()
+        return opt
+
+    a, b = build(Asha, Trial), build(ref.asha.Asha, ref.trial.Trial)
+    rng = random.Random(11)
+    run_a, run_b = [a.get_suggestion() for _ in range(4)], [b.get_suggestion() for _ in range(4)]
+    stream = 0
+    for step in range(400):
+        i = rng.randrange(len(run_a))
+        ta, tb = run_a.pop(i), run_b.pop(i)
+        assert ta.params == tb.params
+        m = rng.random()
+        for t, cls in ((ta, Trial), (tb, ref.trial.Trial)):
+            t.status, t.final_metric = cls.FINALIZED, m
+        a.final_store.append(ta)
+        b.final_store.append(tb)
+        na, nb = a.get_suggestion(ta), b.get_suggestion(tb)
+        assert (na is None) == (nb is None), step
+        if na is None:
+            break
+        assert na.params == nb.params, step      # same configuration AND same budget: fresh vs promoted agree
+        run_a.append(na)
+        run_b.append(nb)
+        stream += 1
+    assert stream >= 5
