@@ -298,3 +298,91 @@ def test_ablation_study_dsl_matches(ref):
         st.model.layers.exclude("dense_2")
         out.append(st.to_dict())
     assert out[0] == out[1]
+
+
+@pytest.mark.parametrize("cfg", [(1, 9, 3, 3), (1, 27, 3, 4), (1, 8, 2, 4)])
+def test_hyperband_pruning_routine_stream_matches(ref, cfg):
+    """Drive both pruners with the same optimizer-side protocol (pruning_routine -> report_trial -> results through
+    the metric getter) on the same metric stream: identical sequence of run requests, promotions, IDLE and end."""
+    from maggy_b200.pruner.hyperband import Hyperband
+
+    mn, mx, eta, n_it = cfg
+    rng = random.Random(5)
+    metrics = {}          # trial id -> metric once "finished"
+    def getter(trial_ids=None):
+        if isinstance(trial_ids, str):
+            return {trial_ids: metrics[trial_ids]} if trial_ids in metrics else {}
+        return {t: metrics[t] for t in (trial_ids or []) if t in metrics}
+
+    a = Hyperband(min_budget=mn, max_budget=mx, eta=eta, n_iterations=n_it, trial_metric_getter=getter)
+    b = ref.hyperband.Hyperband(min_budget=mn, max_budget=mx, eta=eta, n_iterations=n_it, trial_metric_getter=getter)
+    import tempfile
+
+    a.initialize_logger(exp_dir=tempfile.mkdtemp())
+    b.initialize_logger(exp_dir=tempfile.mkdtemp())   # (the reference closes its log file at the end: it must exist)
+    running, counter, log_a, log_b = [], 0, [], []
+    for step in range(2000):
+        ra, rb = a.pruning_routine(), b.pruning_routine()
+        log_a.append(ra if not isinstance(ra, dict) else (ra["trial_id"], ra["budget"]))
+        log_b.append(rb if not isinstance(rb, dict) else (rb["trial_id"], rb["budget"]))
+        assert log_a[-1] == log_b[-1], (step, log_a[-5:], log_b[-5:])
+        if ra is None:
+            break
+        if ra == "IDLE":
+            assert running, "IDLE with nothing in flight"
+            tid = running.pop(rng.randrange(len(running)))
+            metrics[tid] = rng.random()
+            continue
+        counter += 1
+        new_id = f"t{counter:05d}"
+        a.report_trial(original_trial_id=ra["trial_id"], new_trial_id=new_id)
+        b.report_trial(original_trial_id=rb["trial_id"], new_trial_id=new_id)
+        running.append(new_id)
+        if len(running) >= 3:      # three "workers": finish one before asking again
+            tid = running.pop(rng.randrange(len(running)))
+            metrics[tid] = rng.random()
+    assert log_a[-1] is None and counter == a.num_trials() == b.num_trials()
+    assert a.finished() and b.finished()
+
+
+def test_reporter_validation_and_exceptions_match(ref, tmp_path, monkeypatch):
+    from maggy_b200.core import exceptions as ex
+    from maggy_b200.core.environment.singleton import EnvSing
+    from maggy_b200.core.reporter import Reporter
+
+    monkeypatch.setenv("MAGGY_LOG_DIR", str(tmp_path / "log"))
+    EnvSing.reset()
+    rrep = importlib.import_module("maggy.core.reporter").Reporter
+    rex = importlib.import_module("maggy.core.exceptions")
+    ra = Reporter(str(tmp_path / "a.log"), 0, 0, print, None)
+    rb = rrep(str(tmp_path / "b.log"), 0, 0, print)
+    script = [("ok", 0.5, None), ("ok", 0.7, 5), ("bad", "x", None), ("bad", 0.1, "s"), ("bad", 0.2, 3), ("ok", 1, 5),
+              ("ok", 0.9, None)]
+    for kind, metric, step in script:
+        res = []
+        for r in (ra, rb):
+            try:
+                r.broadcast(metric, step)
+                res.append(("ok", r.step, r.metric if not hasattr(r, "_metric_value") else r._metric_value()))
+            except Exception as e:  # noqa: BLE001
+                res.append(("err", type(e).__name__, None))
+        assert res[0] == res[1], (kind, metric, step, res)
+    # early stop: only after a metric was reported, and the next broadcast raises EarlyStopException
+    for r in (ra, rb):
+        r.reset() if not hasattr(r, "trial_id") else None
+    ra.early_stop(), rb.early_stop()
+    assert ra.stop is True and rb.stop is True
+    for r, exc in ((ra, ex.EarlyStopException), (rb, rex.EarlyStopException)):
+        with pytest.raises(exc):
+            r.broadcast(1.0, 99)
+    # same exception vocabulary: constructor arguments, base classes, a ``message`` attribute (the wording is this repo's own)
+    for name, args in (("ReturnTypeError", ("Metric", "x")), ("MetricTypeError", ("Metric", "x")),
+                       ("BroadcastMetricTypeError", ("x",)), ("BroadcastStepTypeError", (0.1, "s")),
+                       ("BroadcastStepValueError", (0.1, 3, 5)), ("BadArgumentsError", ("fn", "a, b")),
+                       ("NotSupportedError", ("category", "value", "suggestion"))):
+        ea, eb = getattr(ex, name)(*args), getattr(rex, name)(*args)
+        assert [c.__name__ for c in type(ea).__mro__[1:]] == [c.__name__ for c in type(eb).__mro__[1:]], name
+        assert isinstance(ea.message, str) and ea.message and isinstance(eb.message, str)
+    assert ex.EarlyStopException(0.5).metric == rex.EarlyStopException(0.5).metric == 0.5
+    ra.close_logger(), rb.close_logger()
+    EnvSing.reset()
