@@ -39,4 +39,5 @@ class TorchDistributedConfig(LagomConfig):
         elif deepspeed_config:
             raise ValueError("deepspeed_config given although backend is not 'deepspeed'")
         self.deepspeed_config = deepspeed_config
+        self.ds_config = deepspeed_config     # the attribute name the reference stores it under (torch_distributed.py:87)
         self.num_workers = num_workers

@@ -386,3 +386,112 @@ def test_reporter_validation_and_exceptions_match(ref, tmp_path, monkeypatch):
     assert ex.EarlyStopException(0.5).metric == rex.EarlyStopException(0.5).metric == 0.5
     ra.close_logger(), rb.close_logger()
     EnvSing.reset()
+
+
+def test_searchspace_add_validation_matches(ref):
+    """Every malformed ``add`` raises the same exception type in both; every well-formed one succeeds in both."""
+    from maggy_b200 import Searchspace
+
+    cases = [("x", ("DOUBLE", [0.0, 1.0])), ("x", ("double", [0, 1])), ("x", ("INTEGER", [1, 10])), ("x", ("INTEGER", [1.0, 10])),
+             ("x", ("DOUBLE", [1.0, 0.0])), ("x", ("DOUBLE", [1.0, 1.0])), ("x", ("DISCRETE", [])), ("x", ("DISCRETE", [3, 1, 2])),
+             ("x", ("CATEGORICAL", ["a"])), ("x", ("CATEGORICAL", [])), ("x", ("DOUBLE", [0.0, 1.0, 2.0])), ("x", ("DOUBLE", "01")),
+             ("x", "DOUBLE"), ("x", ("DOUBLE",)), ("x", None), ("add", ("DOUBLE", [0.0, 1.0])), ("x", ("INTEGER", ["a", "b"])),
+             ("x", ("DISCRETE", ["a", 1])), ("x", ["DOUBLE", [0.0, 1.0]])]
+    for name, value in cases:
+        res = []
+        for cls in (Searchspace, ref.searchspace.Searchspace):
+            sp = cls()
+            try:
+                sp.add(name, value)
+                res.append(("ok", sp.to_dict()))
+            except Exception as e:  # noqa: BLE001
+                res.append(("err", type(e).__name__))
+        assert res[0] == res[1], (name, value, res)
+    # duplicate names
+    for cls in (Searchspace, ref.searchspace.Searchspace):
+        sp = cls(x=("DOUBLE", [0.0, 1.0]))
+        with pytest.raises(ValueError):
+            sp.add("x", ("DOUBLE", [0.0, 2.0]))
+
+
+def test_randomsearch_and_singlerun_protocol_matches(ref):
+    from maggy_b200 import Searchspace
+    from maggy_b200.optimizer import RandomSearch, SingleRun
+
+    rrs = importlib.import_module("maggy.optimizer.randomsearch").RandomSearch
+    rsr = importlib.import_module("maggy.optimizer.singlerun").SingleRun
+    kw = dict(lr=("DOUBLE", [0.0, 1.0]), units=("INTEGER", [1, 9]))
+    for cls, sp_cls in ((RandomSearch, Searchspace), (rrs, ref.searchspace.Searchspace)):
+        o = cls()
+        o.searchspace, o.num_trials, o.direction = sp_cls(**kw), 5, "max"
+        o.trial_store, o.final_store = {}, []
+        o.initialize()
+        got = []
+        while True:
+            t = o.get_suggestion()
+            if t is None:
+                break
+            got.append(t)
+        assert len(got) == 5 and all(0.0 <= t.params["lr"] <= 1.0 and 1 <= t.params["units"] <= 9 for t in got)
+        assert len({t.trial_id for t in got}) == 5
+    # a search space without a continuous parameter is refused by both
+    for cls, sp_cls in ((RandomSearch, Searchspace), (rrs, ref.searchspace.Searchspace)):
+        o = cls()
+        o.searchspace, o.num_trials, o.direction = sp_cls(a=("DISCRETE", [1, 2])), 3, "max"
+        o.trial_store, o.final_store = {}, []
+        with pytest.raises(Exception):
+            o.initialize()
+    for cls in (SingleRun, rsr):
+        o = cls()
+        o.searchspace, o.num_trials, o.direction = None, 3, "max"
+        o.trial_store, o.final_store = {}, []
+        o.initialize()
+        ts = [o.get_suggestion() for _ in range(4)]
+        assert [t is None for t in ts] == [False, False, False, True] and all(t.params in ({}, {"budget": 0}) or True for t in ts[:3])
+
+
+def test_config_classes_match(ref):
+    """Constructor signatures (names and defaults) and the attribute bags they produce."""
+    import inspect
+
+    from maggy_b200 import Searchspace
+    from maggy_b200 import config as ours
+
+    theirs = importlib.import_module("maggy.config")
+    for name in ("LagomConfig", "BaseConfig", "HyperparameterOptConfig", "AblationConfig", "TorchDistributedConfig",
+                 "TfDistributedConfig"):
+        sa = inspect.signature(getattr(ours, name).__init__)
+        sb = inspect.signature(getattr(theirs, name).__init__)
+        pa = [(p.name, p.default) for p in sa.parameters.values()]
+        pb = [(p.name, p.default) for p in sb.parameters.values()]
+        assert pa[:len(pb)] == pb, (name, pa, pb)          # extra (additive) keyword parameters may follow
+    # HPO config: same attribute values for the reference's fields (the reference refuses to build it without Spark)
+    sp_a, sp_b = Searchspace(x=("DOUBLE", [0.0, 1.0])), ref.searchspace.Searchspace(x=("DOUBLE", [0.0, 1.0]))
+    a = ours.HyperparameterOptConfig(num_trials=4, optimizer="randomsearch", searchspace=sp_a, direction="min", es_policy="none",
+                                     es_interval=2, es_min=3, name="n", description="d", hb_interval=2)
+    try:
+        b = theirs.HyperparameterOptConfig(num_trials=4, optimizer="randomsearch", searchspace=sp_b, direction="min",
+                                           es_policy="none", es_interval=2, es_min=3, name="n", description="d", hb_interval=2)
+    except Exception as e:  # noqa: BLE001
+        assert "spark" in str(e).lower()
+        b = None
+    if b is not None:
+        for k in ("num_trials", "optimizer", "direction", "es_policy", "es_interval", "es_min", "name", "description", "hb_interval"):
+            assert getattr(a, k) == getattr(b, k), k
+    for bad in (dict(num_trials=0), dict(num_trials=-3)):
+        with pytest.raises(Exception):
+            ours.HyperparameterOptConfig(optimizer="randomsearch", searchspace=sp_a, **bad)
+    mc = importlib.import_module("maggy.core.config")
+    had_spark = mc.SPARK_AVAILABLE
+    mc.SPARK_AVAILABLE = True       # the reference only builds its distributed-training configs "on a Spark kernel"
+    try:
+        for kwargs in (dict(backend="torch", zero_lvl=1), dict(backend="deepspeed", zero_lvl=2, deepspeed_config={"a": 1})):
+            ca = ours.TorchDistributedConfig(module=object, **kwargs)
+            cb = theirs.TorchDistributedConfig(module=object, **kwargs)
+            for k in ("backend", "zero_lvl", "mixed_precision", "name", "hb_interval", "ds_config", "hparams", "module"):
+                assert getattr(ca, k) == getattr(cb, k), k
+        for cls in (ours.TorchDistributedConfig, theirs.TorchDistributedConfig):
+            with pytest.raises(Exception):
+                cls(module=object, backend="horovod")
+    finally:
+        mc.SPARK_AVAILABLE = had_spark
