@@ -495,3 +495,101 @@ def test_config_classes_match(ref):
                 cls(module=object, backend="horovod")
     finally:
         mc.SPARK_AVAILABLE = had_spark
+
+
+def test_loco_trial_list_matches(ref):
+    """Leave-one-component-out over the same study: same number of trials, same (ablated_feature, ablated_layer) labels,
+    same trial ids, handed out in the same order (custom dataset / base-model generators so no feature store is needed)."""
+    from maggy_b200.ablation import AblationStudy
+    from maggy_b200.ablation.ablator.loco import LOCO
+
+    rab = importlib.import_module("maggy.ablation.ablationstudy").AblationStudy
+    rloco = importlib.import_module("maggy.ablation.ablator.loco").LOCO
+
+    def dataset_gen(ablated_feature=None, **kw):
+        return ablated_feature
+
+    def model_gen():
+        return None
+
+    def custom_model():
+        return None
+
+    seqs = []
+    for study_cls, loco_cls in ((AblationStudy, LOCO), (rab, rloco)):
+        st = study_cls("titanic", 1, label_name="survived", dataset_generator=dataset_gen)
+        st.features.include("age", "fare", "sex")
+        st.model.layers.include("dense_1", "dense_2")
+        st.model.layers.include_groups(["a", "b"], ["c", "d"])
+        st.model.layers.include_groups(prefix="block")
+        st.model.set_base_model_generator(model_gen)
+        st.model.add_custom_model_generator(custom_model, "no_attention")
+        ab = loco_cls(st, [])
+        ab.initialize()
+        assert ab.get_number_of_trials() == 1 + 3 + 2 + 3 + 1
+        seq = []
+        while True:
+            t = ab.get_trial()
+            if t is None:
+                break
+            layer = t.params["ablated_layer"]
+            group = layer.startswith("[")     # a layer group: the reference prints list(set(...)), whose order follows
+            if group:                          # the process' string-hash seed; compare the members, not the print order
+                layer = str(sorted(eval(layer)))
+            seq.append((None if group else t.trial_id, t.params["ablated_feature"], layer, t.trial_type))
+            assert callable(t.params["dataset_function"]) and callable(t.params["model_function"])
+        seqs.append(seq)
+    # (the reference keeps features, layers and groups in sets: its hand-out order depends on the string-hash seed)
+    key = lambda r: tuple("" if x is None else str(x) for x in r)  # noqa: E731
+    assert sorted(seqs[0], key=key) == sorted(seqs[1], key=key) and len(seqs[0]) == 10
+    assert seqs[0][-1][1:3] == ("None", "None") or seqs[0][0][1:3] == ("None", "None")   # the base trial brackets the list
+
+
+def test_abstract_optimizer_helpers_match(ref):
+    """The data-access helpers model-based optimizers build on: hparams / metrics views of the final store (metrics are
+    negated for maximisation), duplicate detection that ignores the budget, trial creation with budgets."""
+    import numpy as np
+
+    from maggy_b200 import Searchspace
+    from maggy_b200.optimizer import RandomSearch
+    from maggy_b200.trial import Trial
+
+    rrs = importlib.import_module("maggy.optimizer.randomsearch").RandomSearch
+    kw = dict(lr=("DOUBLE", [0.0, 1.0]), units=("INTEGER", [1, 9]), act=("CATEGORICAL", ["a", "b"]))
+    out = []
+    for cls, sp_cls, tcls in ((RandomSearch, Searchspace, Trial), (rrs, ref.searchspace.Searchspace, ref.trial.Trial)):
+        o = cls()
+        o.searchspace, o.num_trials, o.direction = sp_cls(**kw), 8, "max"
+        o.trial_store, o.final_store = {}, []
+        o.initialize()
+        rng = random.Random(9)
+        for i in range(6):
+            p = {"lr": rng.random(), "units": rng.randint(1, 9), "act": rng.choice(["a", "b"]), "budget": 1 + (i % 2) * 2}
+            t = tcls(p)
+            for s in range(3):
+                t.append_metric({"value": rng.random(), "step": s})
+            t.status, t.final_metric = tcls.FINALIZED, rng.random()
+            o.final_store.append(t)
+        probe_same = tcls(dict(o.final_store[2].params, budget=99))
+        probe_new = tcls({"lr": 0.123456, "units": 3, "act": "a", "budget": 1})
+        created = o.create_trial({"lr": 0.5, "units": 4, "act": "b"}, sample_type="random", run_budget=3)
+        out.append({
+            "hp_all": np.asarray(o.get_hparams_array()).tolist(), "hp_b1": np.asarray(o.get_hparams_array(budget=1)).tolist(),
+            "m_all": np.asarray(o.get_metrics_array()).tolist(), "m_b3": np.asarray(o.get_metrics_array(budget=3)).tolist(),
+            "m_dict": o.get_metrics_dict(), "hp_dict": o.get_hparams_dict(),
+            "exists": (o.hparams_exist(probe_same), o.hparams_exist(probe_new)),
+            "created": (created.params, created.info_dict.get("sample_type"), created.info_dict.get("run_budget")),
+            "best": (o.ybest(), o.yworst(), o.ymean()), "max_budget": o.get_max_budget(),
+        })
+    def norm(v):
+        if isinstance(v, float):
+            return round(v, 9)
+        if isinstance(v, (list, tuple)):
+            return [norm(x) for x in v]
+        if isinstance(v, dict):
+            return {k: norm(x) for k, x in v.items()}
+        return v
+
+    a, b = out
+    for k in a:
+        assert norm(a[k]) == norm(b[k]), k
