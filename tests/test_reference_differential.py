@@ -593,3 +593,34 @@ def test_abstract_optimizer_helpers_match(ref):
     a, b = out
     for k in a:
         assert norm(a[k]) == norm(b[k]), k
+
+
+@pytest.mark.parametrize("mode", ["dict", "scalar"])
+def test_lagom_base_config_result_matches_end_to_end(mode, tmp_path, monkeypatch):
+    """``lagom(train_fn, BaseConfig)`` run by the reference (own process, its python driver) and here: same result."""
+    import subprocess
+
+    from maggy_b200 import experiment
+    from maggy_b200.config import BaseConfig
+    from maggy_b200.core.environment.singleton import EnvSing
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "helpers", "ref_base_run.py"), str(tmp_path), mode],
+                         capture_output=True, text=True, timeout=300)
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
+    if mode == "scalar":
+        # the reference's base driver only digests dict returns (base_driver.py:231-242 calls .keys() on the value):
+        # a plain number fails there and is averaged here
+        assert not line and "has no attribute 'keys'" in out.stderr
+        monkeypatch.setenv("MAGGY_LOG_DIR", str(tmp_path / "ours"))
+        EnvSing.reset()
+        assert experiment.lagom(lambda: 0.25, BaseConfig(name="diff")) == {"test result": 0.25}
+        EnvSing.reset()
+        return
+    assert line, out.stdout[-2000:] + out.stderr[-2000:]
+    theirs = json.loads(line[-1][len("RESULT "):])
+    monkeypatch.setenv("MAGGY_LOG_DIR", str(tmp_path / "ours"))
+    EnvSing.reset()
+    fn = (lambda: {"accuracy": 0.9, "loss": 0.1}) if mode == "dict" else (lambda: 0.25)
+    ours = experiment.lagom(fn, BaseConfig(name="diff", description="d"))
+    EnvSing.reset()
+    assert json.loads(json.dumps(ours)) == theirs
