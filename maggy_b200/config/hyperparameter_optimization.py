@@ -1,7 +1,7 @@
 """Hyperparameter-optimization config (reference: maggy/config/hyperparameter_optimization.py:33-93)."""
 from __future__ import annotations
 
-from typing import Callable, Optional, Union
+from typing import Optional, Union
 
 from ..earlystop import AbstractEarlyStop
 from ..optimizer import AbstractOptimizer

@@ -8,7 +8,7 @@ is not used).
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Type, Union
+from typing import Optional
 
 from .lagom import LagomConfig
 

@@ -7,14 +7,12 @@ stopping. (The reference class is broken as written — wrong ``_patching_fn`` a
 from __future__ import annotations
 
 import json
-import os
 import threading
 
 from ... import util
 from ...ablation.ablationstudy import AblationStudy
 from ...ablation.ablator import LOCO, AbstractAblator
 from ...earlystop import NoStoppingRule
-from ...trial import Trial
 from .optimization_driver import HyperparameterOptDriver
 
 

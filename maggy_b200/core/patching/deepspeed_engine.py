@@ -18,7 +18,6 @@ kept so that engine.loss_scale / skipped_steps behave as DeepSpeed users expect.
 """
 from __future__ import annotations
 
-import os
 from typing import Optional, Type
 
 import torch

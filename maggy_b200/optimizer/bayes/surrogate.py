@@ -14,7 +14,7 @@ the driver stays on the CPU by design, so both are implemented here from first p
 from __future__ import annotations
 
 import numpy as np
-from scipy.linalg import cho_factor, cho_solve, solve_triangular
+from scipy.linalg import cho_solve, solve_triangular
 from scipy.optimize import fmin_l_bfgs_b
 
 _SQRT5 = np.sqrt(5.0)

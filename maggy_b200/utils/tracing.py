@@ -15,7 +15,6 @@ import json
 import os
 import threading
 import time
-from typing import Optional
 
 _lock = threading.Lock()
 _sink = None          # open file object of this process' trace
