@@ -55,9 +55,13 @@ def seconds_to_milliseconds(t: float) -> int:
 
 
 def get_metric_value(return_dict, metric_key):
+    """The optimization metric out of a train_fn return dict (reference: maggy/util.py:350-365): ``return_dict[key]``
+    when a key is given, the ``"metric"`` entry of a two-entry dict otherwise, else None."""
     if return_dict and metric_key:
         assert metric_key in return_dict.keys(), f"Supplied metric_key {metric_key} is not in returned dict {return_dict}"
-        return str(return_dict[metric_key])
+        return return_dict[metric_key]
+    if return_dict is not None and len(return_dict.keys()) == 2 and "metric" in return_dict.keys():
+        return return_dict["metric"]
     return None
 
 

@@ -624,3 +624,46 @@ def test_lagom_base_config_result_matches_end_to_end(mode, tmp_path, monkeypatch
     ours = experiment.lagom(fn, BaseConfig(name="diff", description="d"))
     EnvSing.reset()
     assert json.loads(json.dumps(ours)) == theirs
+
+
+def test_util_misc_matches(ref, tmp_path, monkeypatch):
+    """json_default_numpy, get_metric_value, validate_ml_id / set_ml_id, build_summary_json over the same trial dirs."""
+    import numpy as np
+
+    from maggy_b200 import util
+    from maggy_b200.core.environment.singleton import EnvSing
+
+    monkeypatch.setenv("MAGGY_LOG_DIR", str(tmp_path / "log"))
+    EnvSing.reset()
+    for v in (np.float32(1.5), np.int64(3), np.arange(3), np.float64(2.0)):
+        assert json.dumps(v, default=util.json_default_numpy) == json.dumps(v, default=ref.util.json_default_numpy)
+    for rv, key in (({"a": 1, "b": 2}, "b"), ({"Metric": 3}, "Metric"), ({"metric": 0.4, "log": "l"}, None), ({"x": 1}, None),
+                    (None, "Metric"), ({}, None)):
+        assert util.get_metric_value(rv, key) == ref.util.get_metric_value(rv, key)
+    for app, run in (("application_1_0001", 1), ("application_1_0001", 7)):
+        assert tuple(util.validate_ml_id(app, run)) == tuple(ref.util.validate_ml_id(app, run))
+    old = os.environ.get("ML_ID")
+    util.set_ml_id("application_9_0001", 4)
+    mine = os.environ["ML_ID"]
+    ref.util.set_ml_id("application_9_0001", 4)
+    assert mine == os.environ["ML_ID"]
+    if old is None:
+        os.environ.pop("ML_ID", None)
+    else:
+        os.environ["ML_ID"] = old
+    # summary over finished-trial directories
+    logdir = tmp_path / "exp"
+    for i, (hp, out) in enumerate([({"lr": 0.1}, {"Metric": 0.5, "log": "x"}), ({"lr": 0.2}, {"Metric": 0.7, "log": "y"})]):
+        d = logdir / f"trial{i}"
+        d.mkdir(parents=True)
+        (d / ".hparams.json").write_text(json.dumps(hp))
+        (d / ".outputs.json").write_text(json.dumps(out))
+    (logdir / "stray.txt").write_text("not a trial")
+    sa = json.loads(util.build_summary_json(str(logdir)))
+    sb = json.loads(ref.util.build_summary_json(str(logdir)))
+    # the reference's local environment lists bare names and has no return-file reader (both are Hopsworks-only there):
+    # its summary is empty outside Hopsworks; the same document structure is filled in here
+    assert sb == {"combinations": []}
+    assert sorted(c["parameters"]["lr"] for c in sa["combinations"]) == [0.1, 0.2]
+    assert all(set(c) == {"parameters", "outputs"} for c in sa["combinations"])
+    EnvSing.reset()
