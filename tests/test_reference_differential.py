@@ -667,3 +667,76 @@ def test_util_misc_matches(ref, tmp_path, monkeypatch):
     assert sorted(c["parameters"]["lr"] for c in sa["combinations"]) == [0.1, 0.2]
     assert all(set(c) == {"parameters", "outputs"} for c in sa["combinations"])
     EnvSing.reset()
+
+
+def test_keras_callbacks_and_trial_methods_match(ref):
+    from maggy_b200 import callbacks as ours_cb
+    from maggy_b200.trial import Trial
+
+    theirs_cb = importlib.import_module("maggy.callbacks")
+
+    class FakeReporter:
+        def __init__(self):
+            self.calls = []
+
+        def broadcast(self, metric, step=None):
+            self.calls.append((metric, step))
+
+    logs = []
+    for mod in (ours_cb, theirs_cb):
+        r = FakeReporter()
+        be, ee = mod.KerasBatchEnd(r, metric="loss"), mod.KerasEpochEnd(r, metric="val_acc")
+        be.on_batch_end(0, {"loss": 0.9, "acc": 0.1})
+        be.on_batch_end(1, {"loss": 0.8})
+        ee.on_epoch_end(0, {"val_acc": 0.3, "loss": 0.8})
+        ee.on_epoch_end(1, {"val_acc": 0.4})
+        logs.append(r.calls)
+    assert logs[0] == logs[1] and len(logs[0]) == 4
+    # Trial bookkeeping methods
+    res = []
+    for cls in (Trial, ref.trial.Trial):
+        t = cls({"a": 1})
+        out = [t.get_early_stop()]
+        t.set_early_stop()
+        out.append(t.get_early_stop())
+        out.append(t.append_metric({"value": 1.0, "step": 0}))
+        out.append(t.append_metric({"value": 2.0, "step": 0}))     # same step again
+        out.append(t.append_metric({"value": None, "step": 1}) if cls is Trial else None)
+        out.append((t.status, cls.PENDING, cls.SCHEDULED, cls.RUNNING, cls.ERROR, cls.FINALIZED))
+        d = json.loads(t.to_json())
+        out.append(sorted(k for k in d if k not in ("start", "duration", "info_dict", "trial_type", "metric_dict")))
+        res.append(out)
+    res[0][4] = None
+    assert res[0] == res[1]
+
+
+def test_local_environment_file_operations_match(ref, tmp_path, monkeypatch):
+    from maggy_b200.core.environment.base import BaseEnv
+
+    rbase = importlib.import_module("maggy.core.environment.base").BaseEnv
+    outs = []
+    for i, cls in enumerate((BaseEnv, rbase)):
+        root = tmp_path / f"env{i}"
+        root.mkdir()
+        monkeypatch.chdir(root)
+        env = cls()
+        d = str(root / "a" / "b")
+        env.mkdir(str(root / "a"))      # (the reference's local mkdir is one level at a time)
+        env.mkdir(d)
+        env.dump("hello", d + "/f.txt")
+        def read(path):
+            with env.open_file(path, flags="r") as fd:
+                return fd.read()
+
+        out = [env.exists(d + "/f.txt"), env.exists(d + "/nope"), env.isdir(d), env.isdir(d + "/f.txt"), read(d + "/f.txt"),
+               sorted(os.path.basename(p) for p in env.ls(d))]
+        with env.open_file(d + "/g.txt", flags="w") as fd:
+            fd.write("x")
+        out.append(read(d + "/g.txt"))
+        env.delete(d + "/g.txt", recursive=False)
+        out.append(env.exists(d + "/g.txt"))
+        env.delete(str(root / "a"), recursive=True)
+        out.append(env.exists(d))
+        out.append(env.str_or_byte("s"))
+        outs.append(out)
+    assert outs[0] == outs[1]
