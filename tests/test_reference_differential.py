@@ -740,3 +740,70 @@ def test_local_environment_file_operations_match(ref, tmp_path, monkeypatch):
         out.append(env.str_or_byte("s"))
         outs.append(out)
     assert outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("interim", [False, True])
+def test_async_bo_training_matrix_matches(ref, interim):
+    """BaseAsyncBO.get_XY — the training matrix every surrogate is fitted on: finished trials, optional interim-result
+    augmentation z = [x, n / N], busy-location imputation — from the same final store / trial store on both sides
+    (a do-nothing surrogate subclass on each)."""
+    import numpy as np
+
+    from maggy_b200 import Searchspace
+    from maggy_b200.optimizer.bayes.base import BaseAsyncBO
+    from maggy_b200.trial import Trial
+
+    rbase = importlib.import_module("maggy.optimizer.bayes.base").BaseAsyncBO
+
+    def make(cls_base):
+        class Dummy(cls_base):
+            def init_model(self):
+                pass
+
+            def update_model(self, budget=0):
+                pass
+
+            def sampling_routine(self, budget=0):
+                return self.searchspace.get_random_parameter_values(1)[0]
+
+            def name(self):
+                return "GP"
+
+            async_strategy, impute_strategy = "impute", "cl_min"
+
+            def impute_metric(self, hparams, budget=0):     # constant liar with the best value so far (gp.py:345-346)
+                return self.ybest(budget)
+        return Dummy
+
+    kw = dict(lr=("DOUBLE", [0.0, 1.0]), units=("INTEGER", [1, 9]), act=("CATEGORICAL", ["a", "b", "c"]))
+    mats = []
+    for base, sp_cls, tcls in ((BaseAsyncBO, Searchspace, Trial), (rbase, ref.searchspace.Searchspace, ref.trial.Trial)):
+        o = make(base)(num_warmup_trials=3, random_fraction=0.0, interim_results=interim, interim_results_interval=2)
+        o.searchspace, o.num_trials, o.direction = sp_cls(**kw), 20, "max"
+        o.trial_store, o.final_store = {}, []
+        o.initialize()
+        rng = random.Random(21)
+        for i in range(7):
+            p = {"lr": rng.random(), "units": rng.randint(1, 9), "act": rng.choice(["a", "b", "c"])}
+            t = (o.create_trial(p, sample_type="random", run_budget=0) if i < 3
+                 else o.create_trial(p, sample_type="model", run_budget=0, model_budget=0))
+            for s in range(6):
+                t.append_metric({"value": rng.random(), "step": s})
+            t.status, t.final_metric = tcls.FINALIZED, rng.random()
+            o.final_store.append(t)
+        for i in range(2):   # two trials still running: their locations get imputed metrics
+            p = {"lr": rng.random(), "units": rng.randint(1, 9), "act": rng.choice(["a", "b", "c"])}
+            t = o.create_trial(p, sample_type="model", run_budget=0, model_budget=0)
+            t.status = tcls.RUNNING
+            o.trial_store[t.trial_id] = t
+        try:
+            X, y = o.get_XY(budget=0, interim_results=interim, interim_results_interval=2)
+        except TypeError:
+            X, y = o.get_XY(budget=0)
+        busy = o.get_busy_locations(budget=0)
+        mats.append((np.asarray(X, dtype=float), np.asarray(y, dtype=float), np.asarray(busy, dtype=object).tolist()))
+    (Xa, ya, ba), (Xb, yb, bb) = mats
+    assert Xa.shape == Xb.shape and ya.shape == yb.shape and len(ba) == len(bb) == 2
+    assert np.allclose(Xa, Xb) and np.allclose(ya, yb)
+    # (numpy turns the reference's mixed-type rows into strings; the values are the same)
+    assert [[str(v) for v in row] for row in ba] == [[str(v) for v in row] for row in bb]
